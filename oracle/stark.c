@@ -1,0 +1,601 @@
+/*
+ * oracle/stark.c -- Merkle tree, FRI, DEEP plumbing, synthetic-segment prover and verifier: CPU restatement.
+ * TEST INFRASTRUCTURE ONLY (see bb.h).
+ *
+ * PARITY UNPINNED: /root/reference holds no STARK golden vectors (SURVEY.md section 0 finding 5) and
+ * the real prover loop is in un-vendored risc0-zkp 3.0.3 (prove/prover.rs, prove/fri.rs, prove/merkle.rs;
+ * Cargo.lock:9155).  This file restates that loop's SHAPE per SURVEY.md Appendix A ("Merkle",
+ * "PolyGroup / commit_group", "FRI", "Prover loop") over a SYNTHETIC circuit: the
+ * rv32im witgen and eval_check (generated code, unavailable) are replaced by a
+ * splitmix64 trace and a degree-4 synthetic constraint so NTT / Poseidon2 / DEEP / FRI run on real data.
+ * What pins it: Poseidon2 KAT, field constants, DFT / fold identities, and oracle_verify(), an
+ * independent verifier that accepts the seal only if every Merkle path, the constraint identity at the
+ * DEEP point, the DEEP quotient at each query and every FRI fold are consistent.
+ *
+ * Reference call sites replaced by this path: prover/crates/workflow/src/tasks/prove.rs:44-52
+ * (prove_segment), :96-104 (lift), tasks/join.rs:52-56 (join), tasks/resolve.rs:84-88, tasks/union.rs:43-47.
+ *
+ * Protocol (all polynomials are the STORED coefficient vectors, i.e. after zk_shift; domain = plain H_4N):
+ *   globals(16 words) -> commit(hash(globals))
+ *   code,data trace -> commit_group each: iNTT(K1), zk_shift(K2), expand+NTT x4 (K3), hash_rows(K4),
+ *        fold tree(K5), write top layer, rng.mix(root)
+ *   accum_mix <- rng; accum Fp4 col k = Fp4(data[4k..4k+3]) * accum_mix^(k+1); commit_group(accum)
+ *   poly_mix <- rng; G(x) = C(Q(x), Q_acc(x/w_N)) evaluated on H_4N, C = sum_k poly_mix^k * term_k with
+ *        terms: products of 4 consecutive columns (k < W/4), then (acc_a(x) - acc_a(x/w_N)) * code_{a mod w_code}(x)
+ *        iNTT(4N) of the 4 Fp planes -> 16 columns x N (column e*4+q = plane e, quarter q) -> commit (no K2)
+ *   z <- rng; coeff_u = [Q_c(z)], [Q_acc_a(z/w_N)], [check_k(z^4)] (K7) -> write, commit(hash)
+ *   mix <- rng; F = sum_points ( sum_t mix^t Q_t(x) - sum_t mix^t u_t ) / (x - point)   (K8)
+ *   FRI on F (K3,K4,K5,K6 per round), final coefficients, 50 queries (K9)
+ */
+#include "oracle.h"
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+static unsigned ilog2(size_t x) { unsigned r = 0; while (((size_t)1 << r) < x) r++; return r; }
+
+/* ------------------------------------------------------------------ Merkle (K4 + K5) */
+void oracle_merkle_build(fp *nodes, const fp *matrix, size_t rows, size_t cols) {
+    oracle_p2_hash_rows(nodes + rows * 8, matrix, rows, cols);
+    for (size_t sz = rows / 2; sz >= 1; sz /= 2) {
+#pragma omp parallel for schedule(static) if (sz >= 1024)
+        for (long j = 0; j < (long)sz; j++) {
+            size_t i = sz + (size_t)j;
+            oracle_p2_hash_pair(nodes + i * 8, nodes + 2 * i * 8, nodes + (2 * i + 1) * 8);
+        }
+    }
+}
+typedef struct { size_t rows, cols; unsigned layers, top_layer; size_t top_size; } merkle_params;
+static merkle_params merkle_params_of(size_t rows, size_t cols) {
+    merkle_params p; p.rows = rows; p.cols = cols; p.layers = ilog2(rows);
+    p.top_layer = p.layers < 5 ? p.layers : 5;         /* floor(log2(50)) = 5 */
+    p.top_size = (size_t)1 << p.top_layer;
+    return p;
+}
+static size_t merkle_proof_words(const merkle_params *p) { return p->cols + (size_t)(p->layers - p->top_layer) * 8; }
+
+/* ------------------------------------------------------------------ transcript */
+typedef struct { uint32_t *buf; size_t pos, cap; oracle_rng rng; } iop_t;
+static void iop_write(iop_t *io, const uint32_t *w, size_t n) {
+    if (io->pos + n > io->cap) { fprintf(stderr, "oracle: seal overflow\n"); abort(); }
+    memcpy(io->buf + io->pos, w, n * 4); io->pos += n;
+}
+static void iop_commit(iop_t *io, const fp *digest8) { oracle_rng_mix(&io->rng, digest8); }
+
+static void merkle_commit(iop_t *io, const fp *nodes, const merkle_params *p) {
+    iop_write(io, nodes + p->top_size * 8, p->top_size * 8);
+    iop_commit(io, nodes + 8);     /* root = nodes[1] */
+}
+static void merkle_prove(iop_t *io, const fp *nodes, const fp *matrix, const merkle_params *p, size_t idx) {
+    for (size_t c = 0; c < p->cols; c++) iop_write(io, &matrix[c * p->rows + idx], 1);
+    idx += p->rows;
+    while (idx >= 2 * p->top_size) { iop_write(io, nodes + (idx ^ 1) * 8, 8); idx >>= 1; }
+}
+
+/* ------------------------------------------------------------------ synthetic witness */
+static inline uint64_t splitmix64_at(uint64_t seed, uint64_t idx) {
+    uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+void oracle_gen_trace(fp *out, uint64_t seed, unsigned po2, size_t cols) {
+    size_t total = cols << po2;
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)total; i++) out[i] = fp_from_u32((uint32_t)(splitmix64_at(seed, (uint64_t)i) % BB_P));
+}
+void oracle_segment_digest(fp *out8, uint64_t seed) {
+    fp w[3] = {(fp)(seed & 0x3FFFFFFF), (fp)((seed >> 30) & 0x3FFFFFFF), (fp)(seed >> 60)};
+    oracle_p2_init();
+    oracle_p2_hash_elems(out8, w, 3);
+}
+/* digest of a seal: view the words as a column-major matrix with 1024 rows (zero padded), hash_rows, fold */
+void oracle_seal_digest(fp *out8, const uint32_t *seal, size_t words) {
+    const size_t rows = 1024;
+    size_t cols = (words + rows - 1) / rows;
+    fp *m = (fp *)calloc(rows * cols, sizeof(fp));
+    memcpy(m, seal, words * 4);
+    fp *nodes = (fp *)malloc(2 * rows * 8 * sizeof(fp));
+    oracle_merkle_build(nodes, m, rows, cols);
+    memcpy(out8, nodes + 8, 32);
+    free(m); free(nodes);
+}
+
+/* ------------------------------------------------------------------ FRI fold (K6) */
+/* in: 4 planes x in_size (bit-reversed coefficients); out: 4 planes x in_size/16 */
+void oracle_fri_fold(fp *out, const fp *in, size_t in_size, fp4 mix) {
+    size_t cnt = in_size / ORACLE_FRI_FOLD;
+#pragma omp parallel for schedule(static) if (cnt >= 4096)
+    for (long idx = 0; idx < (long)cnt; idx++) {
+        fp4 tot = fp4_zero(), cur = fp4_one();
+        for (uint32_t i = 0; i < ORACLE_FRI_FOLD; i++) {
+            size_t j = (size_t)bit_reverse(i, 4) * cnt + (size_t)idx;
+            fp4 f = {{in[j], in[in_size + j], in[2 * in_size + j], in[3 * in_size + j]}};
+            tot = fp4_add(tot, fp4_mul(cur, f));
+            cur = fp4_mul(cur, mix);
+        }
+        for (int e = 0; e < 4; e++) out[(size_t)e * cnt + (size_t)idx] = tot.c[e];
+    }
+}
+
+/* ------------------------------------------------------------------ K7: evaluate bit-reversed coeffs at an Fp4 point */
+static fp4 eval_bitrev(const fp *coeffs, unsigned n, fp4 x) {
+    /* Horner in natural degree order */
+    size_t size = (size_t)1 << n;
+    fp4 acc = fp4_zero();
+    for (size_t d = size; d-- > 0;) {
+        acc = fp4_mul(acc, x);
+        acc.c[0] = fp_add(acc.c[0], coeffs[bit_reverse((uint32_t)d, n)]);
+    }
+    return acc;
+}
+void oracle_batch_evaluate_any(fp4 *out, const fp *coeffs, unsigned n, size_t count, fp4 x) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long c = 0; c < (long)count; c++) out[c] = eval_bitrev(coeffs + ((size_t)c << n), n, x);
+}
+
+/* ------------------------------------------------------------------ seal layout */
+static unsigned fri_rounds(unsigned po2, size_t *final_size) {
+    size_t size = (size_t)1 << po2; unsigned r = 0;
+    while (size > ORACLE_FRI_MIN_DEGREE) { size /= ORACLE_FRI_FOLD; r++; }
+    if (final_size) *final_size = size;
+    return r;
+}
+size_t oracle_seal_words(const oracle_circuit *c) {
+    size_t N = (size_t)1 << c->po2, D = 4 * N;
+    uint32_t W = c->w_code + c->w_data + c->w_accum;
+    uint32_t widths[4] = {c->w_code, c->w_data, c->w_accum, ORACLE_CHECK_COLS};
+    size_t words = ORACLE_GLOBALS;
+    size_t per_query = 0;
+    for (int g = 0; g < 4; g++) {
+        merkle_params p = merkle_params_of(D, widths[g]);
+        words += p.top_size * 8;
+        per_query += merkle_proof_words(&p);
+    }
+    words += (size_t)(W + c->w_accum + ORACLE_CHECK_COLS) * 4;
+    size_t final_size; unsigned rounds = fri_rounds(c->po2, &final_size);
+    size_t size = N;
+    for (unsigned r = 0; r < rounds; r++) {
+        merkle_params p = merkle_params_of(4 * size / ORACLE_FRI_FOLD, 4 * ORACLE_FRI_FOLD);
+        words += p.top_size * 8;
+        per_query += merkle_proof_words(&p);
+        size /= ORACLE_FRI_FOLD;
+    }
+    words += 4 * final_size;
+    words += ORACLE_QUERIES * per_query;
+    return words;
+}
+
+/* ------------------------------------------------------------------ prover */
+typedef struct { size_t cols; fp *coeffs; fp *evals; fp *nodes; merkle_params mp; } group_t;
+
+static void commit_group(iop_t *io, group_t *g, unsigned po2, int do_interp_shift) {
+    size_t N = (size_t)1 << po2, D = 4 * N;
+    if (do_interp_shift) {
+        oracle_batch_interpolate_ntt(g->coeffs, po2, g->cols);   /* K1 */
+        oracle_batch_zk_shift(g->coeffs, po2, g->cols);          /* K2 */
+    }
+    g->evals = (fp *)malloc(g->cols * D * sizeof(fp));
+    oracle_batch_expand_into_evaluate_ntt(g->evals, g->coeffs, po2, g->cols, ORACLE_INV_RATE_LOG);   /* K3 */
+    g->mp = merkle_params_of(D, g->cols);
+    g->nodes = (fp *)malloc(2 * D * 8 * sizeof(fp));
+    oracle_merkle_build(g->nodes, g->evals, D, g->cols);         /* K4 + K5 */
+    merkle_commit(io, g->nodes, &g->mp);
+}
+static void group_free(group_t *g) { free(g->coeffs); free(g->evals); free(g->nodes); }
+
+static int check_circuit(const oracle_circuit *c) {
+    if (c->po2 < 9 || c->po2 > 22) return 1;
+    if (c->w_code == 0 || c->w_code % 4 || c->w_data % 4 || c->w_accum % 4 || c->w_accum == 0) return 1;
+    if (c->w_accum > c->w_data) return 1;
+    if (c->w_code + c->w_data + c->w_accum > 512) return 1;
+    return 0;
+}
+
+int oracle_prove(const oracle_circuit *c, uint64_t seed, const fp *input_digest8, const fp *trace, uint32_t *seal) {
+    if (check_circuit(c)) return 1;
+    oracle_p2_init();
+    const unsigned po2 = c->po2;
+    const size_t N = (size_t)1 << po2, D = 4 * N;
+    const uint32_t W = c->w_code + c->w_data + c->w_accum;
+    const uint32_t T = W + c->w_accum + ORACLE_CHECK_COLS;
+    oracle_ntt_prepare(po2 + 2);
+
+    iop_t io; io.buf = seal; io.pos = 0; io.cap = oracle_seal_words(c); oracle_rng_init(&io.rng);
+
+    /* globals */
+    uint32_t globals[ORACLE_GLOBALS] = {c->po2, c->w_code, c->w_data, c->w_accum, c->kind, 0, 0, 0};
+    memcpy(globals + 8, input_digest8, 32);
+    iop_write(&io, globals, ORACLE_GLOBALS);
+    { fp d[8]; oracle_p2_hash_elems(d, globals, ORACLE_GLOBALS); iop_commit(&io, d); }
+
+    /* code + data trace (witgen stand-in), commit */
+    group_t grp[4]; memset(grp, 0, sizeof grp);
+    grp[0].cols = c->w_code; grp[1].cols = c->w_data; grp[2].cols = c->w_accum; grp[3].cols = ORACLE_CHECK_COLS;
+    grp[0].coeffs = (fp *)malloc(grp[0].cols * N * sizeof(fp));
+    grp[1].coeffs = (fp *)malloc(grp[1].cols * N * sizeof(fp));
+    if (trace) {
+        memcpy(grp[0].coeffs, trace, grp[0].cols * N * sizeof(fp));
+        memcpy(grp[1].coeffs, trace + grp[0].cols * N, grp[1].cols * N * sizeof(fp));
+    } else {
+        fp *tmp = (fp *)malloc((size_t)(c->w_code + c->w_data) * N * sizeof(fp));
+        oracle_gen_trace(tmp, seed, po2, c->w_code + c->w_data);
+        memcpy(grp[0].coeffs, tmp, grp[0].cols * N * sizeof(fp));
+        memcpy(grp[1].coeffs, tmp + grp[0].cols * N, grp[1].cols * N * sizeof(fp));
+        free(tmp);
+    }
+    /* accum needs the raw data trace: compute after the mix but from a copy taken now */
+    fp *data_raw = (fp *)malloc((size_t)c->w_accum * N * sizeof(fp));
+    memcpy(data_raw, grp[1].coeffs, (size_t)c->w_accum * N * sizeof(fp));
+    commit_group(&io, &grp[0], po2, 1);
+    commit_group(&io, &grp[1], po2, 1);
+
+    /* accumulate stand-in */
+    fp4 accum_mix = oracle_rng_ext(&io.rng);
+    grp[2].coeffs = (fp *)malloc(grp[2].cols * N * sizeof(fp));
+    {
+        fp4 pw = accum_mix;
+        for (uint32_t k = 0; k < c->w_accum / 4; k++) {
+#pragma omp parallel for schedule(static)
+            for (long j = 0; j < (long)N; j++) {
+                fp4 d = {{data_raw[(4 * k + 0) * N + j], data_raw[(4 * k + 1) * N + j],
+                          data_raw[(4 * k + 2) * N + j], data_raw[(4 * k + 3) * N + j]}};
+                fp4 a = fp4_mul(d, pw);
+                for (int e = 0; e < 4; e++) grp[2].coeffs[(4 * k + e) * N + j] = a.c[e];
+            }
+            pw = fp4_mul(pw, accum_mix);
+        }
+    }
+    free(data_raw);
+    commit_group(&io, &grp[2], po2, 1);
+
+    /* eval_check stand-in over the 4N domain */
+    fp4 poly_mix = oracle_rng_ext(&io.rng);
+    const uint32_t n_terms = W / 4 + c->w_accum;
+    fp4 *pmix = (fp4 *)malloc(n_terms * sizeof(fp4));
+    pmix[0] = fp4_one();
+    for (uint32_t k = 1; k < n_terms; k++) pmix[k] = fp4_mul(pmix[k - 1], poly_mix);
+    fp *check_planes = (fp *)malloc(4 * D * sizeof(fp));
+    {
+        const fp *ecode = grp[0].evals, *edata = grp[1].evals, *eacc = grp[2].evals;
+#pragma omp parallel for schedule(static)
+        for (long i = 0; i < (long)D; i++) {
+            fp u[1024];
+            uint32_t w = 0;
+            for (uint32_t k = 0; k < c->w_code; k++) u[w++] = ecode[k * D + i];
+            for (uint32_t k = 0; k < c->w_data; k++) u[w++] = edata[k * D + i];
+            for (uint32_t k = 0; k < c->w_accum; k++) u[w++] = eacc[k * D + i];
+            fp4 tot = fp4_zero();
+            for (uint32_t k = 0; k < W / 4; k++) {
+                fp t = fp_mul(fp_mul(u[4 * k], u[4 * k + 1]), fp_mul(u[4 * k + 2], u[4 * k + 3]));
+                tot = fp4_add(tot, fp4_mul_fp(pmix[k], t));
+            }
+            size_t ib = ((size_t)i + D - 4) & (D - 1);
+            for (uint32_t a = 0; a < c->w_accum; a++) {
+                fp t = fp_mul(fp_sub(eacc[a * D + i], eacc[a * D + ib]), ecode[(a % c->w_code) * D + i]);
+                tot = fp4_add(tot, fp4_mul_fp(pmix[W / 4 + a], t));
+            }
+            for (int e = 0; e < 4; e++) check_planes[(size_t)e * D + i] = tot.c[e];
+        }
+    }
+    free(pmix);
+    oracle_batch_interpolate_ntt(check_planes, po2 + 2, 4);
+    grp[3].coeffs = check_planes;      /* 4 planes x 4N reinterpreted as 16 columns x N */
+    commit_group(&io, &grp[3], po2, 0);
+
+    /* DEEP point, tap evaluations (K7) */
+    fp4 z = oracle_rng_ext(&io.rng);
+    fp4 z_back = fp4_mul_fp(z, oracle_rou_rev(po2));
+    fp4 z4 = fp4_pow(z, 4);
+    fp4 *u = (fp4 *)malloc(T * sizeof(fp4));
+    oracle_batch_evaluate_any(u, grp[0].coeffs, po2, c->w_code, z);
+    oracle_batch_evaluate_any(u + c->w_code, grp[1].coeffs, po2, c->w_data, z);
+    oracle_batch_evaluate_any(u + c->w_code + c->w_data, grp[2].coeffs, po2, c->w_accum, z);
+    oracle_batch_evaluate_any(u + W, grp[2].coeffs, po2, c->w_accum, z_back);
+    oracle_batch_evaluate_any(u + W + c->w_accum, grp[3].coeffs, po2, ORACLE_CHECK_COLS, z4);
+    iop_write(&io, (const uint32_t *)u, (size_t)T * 4);
+    { fp d[8]; oracle_p2_hash_elems(d, (const fp *)u, (size_t)T * 4); iop_commit(&io, d); }
+
+    /* DEEP combination (K8) */
+    fp4 mix = oracle_rng_ext(&io.rng);
+    fp4 *mp = (fp4 *)malloc(T * sizeof(fp4));
+    mp[0] = fp4_one();
+    for (uint32_t t = 1; t < T; t++) mp[t] = fp4_mul(mp[t - 1], mix);
+    fp *fplanes = (fp *)calloc(4 * N, sizeof(fp));     /* F, 4 planes x N, bit-reversed */
+    {
+        fp4 *combo = (fp4 *)malloc(N * sizeof(fp4));
+        fp4 *quot = (fp4 *)malloc(N * sizeof(fp4));
+        fp4 *F = (fp4 *)calloc(N, sizeof(fp4));
+        for (int pt = 0; pt < 3; pt++) {
+            fp4 point = pt == 0 ? z : (pt == 1 ? z_back : z4);
+            const fp *src; uint32_t ncol, t0;
+            /* natural-degree-order combination: combo[d] = sum_t mix^t * coeff_t[bitrev(d)] */
+#pragma omp parallel for schedule(static)
+            for (long d = 0; d < (long)N; d++) {
+                size_t j = bit_reverse((uint32_t)d, po2);
+                fp4 acc = fp4_zero();
+                if (pt == 0) {
+                    uint32_t t = 0;
+                    for (int g = 0; g < 3; g++)
+                        for (size_t k = 0; k < grp[g].cols; k++, t++)
+                            acc = fp4_add(acc, fp4_mul_fp(mp[t], grp[g].coeffs[k * N + j]));
+                } else if (pt == 1) {
+                    for (size_t k = 0; k < grp[2].cols; k++)
+                        acc = fp4_add(acc, fp4_mul_fp(mp[W + k], grp[2].coeffs[k * N + j]));
+                } else {
+                    for (size_t k = 0; k < ORACLE_CHECK_COLS; k++)
+                        acc = fp4_add(acc, fp4_mul_fp(mp[W + c->w_accum + k], grp[3].coeffs[k * N + j]));
+                }
+                combo[d] = acc;
+            }
+            (void)src; (void)ncol; (void)t0;
+            /* subtract the u-constant */
+            uint32_t lo = pt == 0 ? 0 : (pt == 1 ? W : W + c->w_accum);
+            uint32_t hi = pt == 0 ? W : (pt == 1 ? W + c->w_accum : T);
+            fp4 usum = fp4_zero();
+            for (uint32_t t = lo; t < hi; t++) usum = fp4_add(usum, fp4_mul(mp[t], u[t]));
+            combo[0] = fp4_sub(combo[0], usum);
+            /* synthetic division by (x - point) */
+            fp4 carry = fp4_zero();
+            for (size_t d = N; d-- > 0;) {
+                quot[d] = carry;                                   /* b_d ... stored shifted: quot[d] = b_d */
+                carry = fp4_add(combo[d], fp4_mul(carry, point));  /* b_{d-1} = c_d + point*b_d */
+            }
+            if (!fp4_eq(carry, fp4_zero())) { fprintf(stderr, "oracle: DEEP remainder nonzero (pt %d)\n", pt); return 2; }
+            for (size_t d = 0; d < N; d++) F[d] = fp4_add(F[d], quot[d]);
+        }
+        for (size_t d = 0; d < N; d++) {
+            size_t j = bit_reverse((uint32_t)d, po2);
+            for (int e = 0; e < 4; e++) fplanes[(size_t)e * N + j] = F[d].c[e];
+        }
+        free(combo); free(quot); free(F);
+    }
+    free(mp); free(u);
+
+    /* FRI commit phase */
+    size_t final_size; unsigned rounds = fri_rounds(po2, &final_size);
+    group_t fr[8]; memset(fr, 0, sizeof fr);
+    fp *cur = fplanes; size_t size = N; unsigned lg = po2;
+    for (unsigned r = 0; r < rounds; r++) {
+        fr[r].cols = 4 * ORACLE_FRI_FOLD;
+        fr[r].coeffs = cur;
+        size_t dom = 4 * size;
+        fr[r].evals = (fp *)malloc(4 * dom * sizeof(fp));
+        oracle_batch_expand_into_evaluate_ntt(fr[r].evals, cur, lg, 4, ORACLE_INV_RATE_LOG);
+        size_t rows = dom / ORACLE_FRI_FOLD;
+        fr[r].mp = merkle_params_of(rows, fr[r].cols);
+        fr[r].nodes = (fp *)malloc(2 * rows * 8 * sizeof(fp));
+        oracle_merkle_build(fr[r].nodes, fr[r].evals, rows, fr[r].cols);
+        merkle_commit(&io, fr[r].nodes, &fr[r].mp);
+        fp4 fmix = oracle_rng_ext(&io.rng);
+        fp *next = (fp *)malloc(4 * (size / ORACLE_FRI_FOLD) * sizeof(fp));
+        oracle_fri_fold(next, cur, size, fmix);
+        cur = next; size /= ORACLE_FRI_FOLD; lg -= 4;
+    }
+    iop_write(&io, cur, 4 * size);
+    { fp d[8]; oracle_p2_hash_elems(d, cur, 4 * size); iop_commit(&io, d); }
+
+    /* query phase (K9) */
+    for (int q = 0; q < ORACLE_QUERIES; q++) {
+        size_t pos = oracle_rng_bits(&io.rng, po2 + 2) & (D - 1);
+        for (int g = 0; g < 4; g++) merkle_prove(&io, grp[g].nodes, grp[g].evals, &grp[g].mp, pos);
+        size_t dom = D;
+        for (unsigned r = 0; r < rounds; r++) {
+            size_t rows = dom / ORACLE_FRI_FOLD;
+            size_t group = pos % rows;
+            merkle_prove(&io, fr[r].nodes, fr[r].evals, &fr[r].mp, group);
+            pos = group; dom = rows;
+        }
+    }
+    int rc = io.pos == io.cap ? 0 : 3;
+    for (unsigned r = 0; r < rounds; r++) { free(fr[r].evals); free(fr[r].nodes); if (r > 0) free(fr[r].coeffs); }
+    if (rounds > 0) free(cur);
+    free(fplanes);
+    for (int g = 0; g < 4; g++) group_free(&grp[g]);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ verifier (independent replay) */
+typedef struct { const uint32_t *buf; size_t pos, cap; oracle_rng rng; int bad; } rd_t;
+static const uint32_t *rd_take(rd_t *r, size_t n) {
+    static const uint32_t zeros[4096] = {0};
+    if (r->pos + n > r->cap) { r->bad = 1; return zeros; }
+    const uint32_t *p = r->buf + r->pos; r->pos += n; return p;
+}
+static int valid_elems(const uint32_t *w, size_t n) { for (size_t i = 0; i < n; i++) if (w[i] >= BB_P) return 0; return 1; }
+
+typedef struct { merkle_params mp; const fp *top; fp root[8]; } vmerkle_t;
+static void vmerkle_read(rd_t *r, vmerkle_t *m, size_t rows, size_t cols) {
+    m->mp = merkle_params_of(rows, cols);
+    m->top = rd_take(r, m->mp.top_size * 8);
+    /* fold the top layer down to the root */
+    fp tmp[64 * 8];
+    memcpy(tmp + m->mp.top_size * 8, m->top, m->mp.top_size * 32);
+    for (size_t i = m->mp.top_size - 1; i >= 1; i--) oracle_p2_hash_pair(tmp + i * 8, tmp + 2 * i * 8, tmp + (2 * i + 1) * 8);
+    if (m->mp.top_size == 1) memcpy(m->root, m->top, 32); else memcpy(m->root, tmp + 8, 32);
+    oracle_rng_mix(&r->rng, m->root);
+}
+/* returns pointer to the opened leaf values or NULL on failure */
+static const fp *vmerkle_verify(rd_t *r, const vmerkle_t *m, size_t idx) {
+    const fp *vals = rd_take(r, m->mp.cols);
+    if (!valid_elems(vals, m->mp.cols)) return NULL;
+    fp cur[8];
+    oracle_p2_hash_elems(cur, vals, m->mp.cols);
+    idx += m->mp.rows;
+    while (idx >= 2 * m->mp.top_size) {
+        const fp *sib = rd_take(r, 8);
+        fp nxt[8];
+        if (idx & 1) oracle_p2_hash_pair(nxt, sib, cur); else oracle_p2_hash_pair(nxt, cur, sib);
+        memcpy(cur, nxt, 32);
+        idx >>= 1;
+    }
+    if (memcmp(cur, m->top + (idx - m->mp.top_size) * 8, 32) != 0) return NULL;
+    return vals;
+}
+
+int oracle_verify(const uint32_t *seal, size_t words) {
+    oracle_p2_init();
+    if (words < ORACLE_GLOBALS) return 100;
+    oracle_circuit c = {seal[0], seal[1], seal[2], seal[3], seal[4]};
+    if (check_circuit(&c)) return 101;
+    if (oracle_seal_words(&c) != words) return 102;
+    const unsigned po2 = c.po2;
+    const size_t N = (size_t)1 << po2, D = 4 * N;
+    const uint32_t W = c.w_code + c.w_data + c.w_accum, T = W + c.w_accum + ORACLE_CHECK_COLS;
+    uint32_t widths[4] = {c.w_code, c.w_data, c.w_accum, ORACLE_CHECK_COLS};
+    rd_t r; r.buf = seal; r.pos = 0; r.cap = words; r.bad = 0; oracle_rng_init(&r.rng);
+
+    const uint32_t *globals = rd_take(&r, ORACLE_GLOBALS);
+    if (!valid_elems(globals, ORACLE_GLOBALS)) return 103;
+    { fp d[8]; oracle_p2_hash_elems(d, globals, ORACLE_GLOBALS); oracle_rng_mix(&r.rng, d); }
+
+    vmerkle_t vm[4];
+    vmerkle_read(&r, &vm[0], D, widths[0]);
+    vmerkle_read(&r, &vm[1], D, widths[1]);
+    fp4 accum_mix = oracle_rng_ext(&r.rng); (void)accum_mix;   /* binds the transcript; accum itself is witness */
+    vmerkle_read(&r, &vm[2], D, widths[2]);
+    fp4 poly_mix = oracle_rng_ext(&r.rng);
+    vmerkle_read(&r, &vm[3], D, widths[3]);
+    fp4 z = oracle_rng_ext(&r.rng);
+    fp4 z_back = fp4_mul_fp(z, oracle_rou_rev(po2));
+    fp4 z4 = fp4_pow(z, 4);
+    const fp4 *u = (const fp4 *)rd_take(&r, (size_t)T * 4);
+    if (!valid_elems((const uint32_t *)u, (size_t)T * 4)) return 104;
+    { fp d[8]; oracle_p2_hash_elems(d, (const fp *)u, (size_t)T * 4); oracle_rng_mix(&r.rng, d); }
+
+    /* constraint identity at the DEEP point: C(u) == sum_e X^e sum_q z^{rev2(q)} check[e*4+q](z^4) */
+    {
+        fp4 lhs = fp4_zero(), pw = fp4_one();
+        for (uint32_t k = 0; k < W / 4; k++) {
+            fp4 t = fp4_mul(fp4_mul(u[4 * k], u[4 * k + 1]), fp4_mul(u[4 * k + 2], u[4 * k + 3]));
+            lhs = fp4_add(lhs, fp4_mul(pw, t));
+            pw = fp4_mul(pw, poly_mix);
+        }
+        const fp4 *uacc = u + c.w_code + c.w_data, *uback = u + W;
+        for (uint32_t a = 0; a < c.w_accum; a++) {
+            fp4 t = fp4_mul(fp4_sub(uacc[a], uback[a]), u[a % c.w_code]);
+            lhs = fp4_add(lhs, fp4_mul(pw, t));
+            pw = fp4_mul(pw, poly_mix);
+        }
+        const fp4 *uchk = u + W + c.w_accum;
+        fp4 zp[4]; zp[0] = fp4_one(); for (int k = 1; k < 4; k++) zp[k] = fp4_mul(zp[k - 1], z);
+        fp4 rhs = fp4_zero();
+        for (int e = 0; e < 4; e++) {
+            fp4 inner = fp4_zero();
+            for (uint32_t q = 0; q < 4; q++) inner = fp4_add(inner, fp4_mul(zp[bit_reverse(q, 2)], uchk[e * 4 + q]));
+            fp4 basis = fp4_zero(); basis.c[e] = fp_from_u32(1);
+            rhs = fp4_add(rhs, fp4_mul(basis, inner));
+        }
+        if (!fp4_eq(lhs, rhs)) return 110;
+    }
+
+    fp4 mix = oracle_rng_ext(&r.rng);
+    fp4 *mp = (fp4 *)malloc(T * sizeof(fp4));
+    mp[0] = fp4_one();
+    for (uint32_t t = 1; t < T; t++) mp[t] = fp4_mul(mp[t - 1], mix);
+    fp4 usum[3] = {fp4_zero(), fp4_zero(), fp4_zero()};
+    for (uint32_t t = 0; t < T; t++) {
+        int pt = t < W ? 0 : (t < W + c.w_accum ? 1 : 2);
+        usum[pt] = fp4_add(usum[pt], fp4_mul(mp[t], u[t]));
+    }
+
+    /* FRI commit phase */
+    size_t final_size; unsigned rounds = fri_rounds(po2, &final_size);
+    vmerkle_t fm[8]; fp4 fmix[8];
+    size_t size = N;
+    for (unsigned k = 0; k < rounds; k++) {
+        vmerkle_read(&r, &fm[k], 4 * size / ORACLE_FRI_FOLD, 4 * ORACLE_FRI_FOLD);
+        fmix[k] = oracle_rng_ext(&r.rng);
+        size /= ORACLE_FRI_FOLD;
+    }
+    const fp *final_coeffs = rd_take(&r, 4 * final_size);
+    if (!valid_elems(final_coeffs, 4 * final_size)) { free(mp); return 105; }
+    { fp d[8]; oracle_p2_hash_elems(d, final_coeffs, 4 * final_size); oracle_rng_mix(&r.rng, d); }
+    const unsigned final_lg = ilog2(final_size);
+
+    int rc = 0;
+    const fp inv16 = fp_inv(fp_from_u32(16));
+    for (int q = 0; q < ORACLE_QUERIES && !rc; q++) {
+        size_t pos = oracle_rng_bits(&r.rng, po2 + 2) & (D - 1);
+        const fp *leaf[4];
+        for (int g = 0; g < 4; g++) { leaf[g] = vmerkle_verify(&r, &vm[g], pos); if (!leaf[g]) { rc = 120 + g; break; } }
+        if (rc) break;
+        /* DEEP value at x = w_4N^pos */
+        fp x = fp_pow(oracle_rou_fwd(po2 + 2), pos);
+        fp4 num[3] = {fp4_zero(), fp4_zero(), fp4_zero()};
+        uint32_t t = 0;
+        for (int g = 0; g < 3; g++) for (uint32_t k = 0; k < widths[g]; k++, t++) num[0] = fp4_add(num[0], fp4_mul_fp(mp[t], leaf[g][k]));
+        for (uint32_t k = 0; k < c.w_accum; k++) num[1] = fp4_add(num[1], fp4_mul_fp(mp[W + k], leaf[2][k]));
+        for (uint32_t k = 0; k < ORACLE_CHECK_COLS; k++) num[2] = fp4_add(num[2], fp4_mul_fp(mp[W + c.w_accum + k], leaf[3][k]));
+        fp4 pts[3] = {z, z_back, z4};
+        fp4 expect = fp4_zero();
+        for (int pt = 0; pt < 3; pt++) {
+            fp4 den = fp4_sub(fp4_from_fp(x), pts[pt]);
+            expect = fp4_add(expect, fp4_mul(fp4_sub(num[pt], usum[pt]), fp4_inv(den)));
+        }
+        /* FRI rounds */
+        size_t dom = D;
+        for (unsigned k = 0; k < rounds; k++) {
+            size_t rows = dom / ORACLE_FRI_FOLD;
+            size_t group = pos % rows, quot = pos / rows;
+            const fp *lv = vmerkle_verify(&r, &fm[k], group);
+            if (!lv) { rc = 130 + (int)k; break; }
+            /* leaf column e*16 + kk = plane e at position group + kk*rows */
+            fp4 f[16];
+            for (int kk = 0; kk < 16; kk++) for (int e = 0; e < 4; e++) f[kk].c[e] = lv[e * 16 + kk];
+            if (!fp4_eq(f[quot], expect)) { rc = 140 + (int)k; break; }
+            /* fold: P_i(y) = 1/16 sum_kk (x zeta^kk)^-i f(x zeta^kk), y = x^16; next = sum_i mix^i P_i */
+            unsigned lgdom = ilog2(dom);
+            fp xg = fp_pow(oracle_rou_fwd(lgdom), group);
+            fp zeta = oracle_rou_fwd(4);
+            fp xinv[16];
+            { fp cx = fp_inv(xg), zi = fp_inv(zeta), cz = fp_from_u32(1);
+              for (int kk = 0; kk < 16; kk++) { xinv[kk] = fp_mul(cx, cz); cz = fp_mul(cz, zi); } }
+            fp4 next = fp4_zero(), mpw = fp4_one();
+            for (int i = 0; i < 16; i++) {
+                fp4 Pi = fp4_zero();
+                for (int kk = 0; kk < 16; kk++) Pi = fp4_add(Pi, fp4_mul_fp(f[kk], fp_pow(xinv[kk], (uint64_t)i)));
+                Pi = fp4_mul_fp(Pi, inv16);
+                next = fp4_add(next, fp4_mul(mpw, Pi));
+                mpw = fp4_mul(mpw, fmix[k]);
+            }
+            expect = next; pos = group; dom = rows;
+        }
+        if (rc) break;
+        /* final polynomial at x = w_dom^pos */
+        {
+            unsigned lgdom = ilog2(dom);
+            fp4 xf = fp4_from_fp(fp_pow(oracle_rou_fwd(lgdom), pos));
+            fp4 val = fp4_zero();
+            for (int e = 0; e < 4; e++) {
+                fp4 pe = eval_bitrev(final_coeffs + (size_t)e * final_size, final_lg, xf);
+                fp4 basis = fp4_zero(); basis.c[e] = fp_from_u32(1);
+                val = fp4_add(val, fp4_mul(basis, pe));
+            }
+            if (!fp4_eq(val, expect)) { rc = 150; break; }
+        }
+    }
+    free(mp);
+    if (rc) return rc;
+    if (r.bad || r.pos != r.cap) return 160;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ self-test of the pins */
+int oracle_selftest(void) {
+    static const uint32_t KAT[24] = {
+        0x2ed3e23d, 0x12921fb0, 0x0e659e79, 0x61d81dc9, 0x32bae33b, 0x62486ae3, 0x1e681b60, 0x24b91325,
+        0x2a2ef5b9, 0x50e8593e, 0x5bc818ec, 0x10691997, 0x35a14520, 0x2ba6a3c5, 0x279d47ec, 0x55014e81,
+        0x5953a67f, 0x2f403111, 0x6b8828ff, 0x1801301f, 0x2749207a, 0x3dc9cf21, 0x3c985ba2, 0x57a99864};
+    oracle_p2_init();
+    fp st[24];
+    for (uint32_t i = 0; i < 24; i++) st[i] = fp_from_u32(i);
+    oracle_p2_mix(st);
+    for (int i = 0; i < 24; i++) if (fp_to_u32(st[i]) != KAT[i]) return 1;
+    if (fp_to_u32(oracle_rou_fwd(27)) != 137) return 2;
+    if (fp_to_u32(fp_pow(oracle_rou_fwd(27), 1u << 26)) != BB_P - 1) return 3;
+    if (fp_from_u32(1) != 268435454u) return 4;
+    fp4 a = {{fp_from_u32(3), fp_from_u32(5), fp_from_u32(7), fp_from_u32(11)}};
+    if (!fp4_eq(fp4_mul(a, fp4_inv(a)), fp4_one())) return 5;
+    return 0;
+}
