@@ -1,0 +1,100 @@
+// BabyBear (p = 15*2^27+1) Montgomery arithmetic and the degree-4 extension for sm_100a.
+//
+// Replaces the device field code of risc0-sys 1.5.0 / sppark 0.1.14 (un-vendored CUDA behind
+// risc0_zkvm::ProverServer; reached from /root/reference/prover/crates/workflow/src/tasks/prove.rs:44-52).
+// Representation is identical to the reference's: u32 Montgomery form a*2^32 mod p, canonical in [0,p),
+// so buffers are interchangeable with a risc0 `DeviceBuffer<BabyBearElem>` (SURVEY.md 8b "Data layout").
+//
+// Instruction budget (checked with cuobjdump -sass): mul = IMAD.WIDE.U32 + IMAD + IMAD.HI.U32 + IADD + VIADDMNMX.U32,
+// add/sub = IADD + VIADDMNMX.U32 (the DPX fused add-min removes the compare/select pair).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+constexpr uint32_t P = 2013265921u;        // 0x78000001
+constexpr uint32_t PINV = 0x88000001u;     // p^-1 mod 2^32
+constexpr uint32_t R1 = 268435454u;        // 2^32 mod p  (Montgomery one)
+constexpr uint32_t R2 = 1172168163u;       // 2^64 mod p
+constexpr uint32_t NBETA_M = 1073741848u;  // mont(p - 11): X^4 = -11
+
+// min(x + y, z) as one VIADDMNMX on sm_90+/sm_100
+__device__ __forceinline__ uint32_t addmin(uint32_t x, uint32_t y, uint32_t z) { return __viaddmin_u32(x, y, z); }
+
+__device__ __forceinline__ uint32_t fp_add(uint32_t a, uint32_t b) {
+    uint32_t s = a + b;                     // < 2p < 2^32
+    return addmin(s, 0u - P, s);            // min(s - p, s): s - p wraps high when s < p
+}
+__device__ __forceinline__ uint32_t fp_sub(uint32_t a, uint32_t b) {
+    uint32_t d = a - b;                     // wraps high when a < b
+    return addmin(d, P, d);                 // min(d + p, d)
+}
+__device__ __forceinline__ uint32_t fp_neg(uint32_t a) { return a ? P - a : 0u; }
+__device__ __forceinline__ uint32_t fp_dbl(uint32_t a) { return fp_add(a, a); }
+
+// Montgomery reduction of T < p*2^32 given as (hi, lo): returns T / 2^32 mod p, canonical.
+__device__ __forceinline__ uint32_t fp_redc(uint32_t hi, uint32_t lo) {
+    uint32_t m = lo * PINV;                 // m*p == lo (mod 2^32)
+    uint32_t t = __umulhi(m, P);            // (T - m*p) / 2^32 = hi - t, in (-p, p)
+    uint32_t r = hi - t;
+    return addmin(r, P, r);                 // min(r + p, r)
+}
+__device__ __forceinline__ uint32_t fp_mul(uint32_t a, uint32_t b) {
+    uint64_t o = (uint64_t)a * b;
+    return fp_redc((uint32_t)(o >> 32), (uint32_t)o);
+}
+// a*b + c*2^32-ish accumulate: returns (a*b + acc64) / 2^32 mod p; caller guarantees a*b + acc64 < p*2^32
+__device__ __forceinline__ uint32_t fp_mul_acc(uint32_t a, uint32_t b, uint64_t acc64) {
+    uint64_t o = (uint64_t)a * b + acc64;
+    return fp_redc((uint32_t)(o >> 32), (uint32_t)o);
+}
+__device__ __forceinline__ uint32_t fp_sqr(uint32_t a) { return fp_mul(a, a); }
+__device__ __forceinline__ uint32_t fp_to_mont(uint32_t x) { return fp_mul(x, R2); }      // x < p
+__device__ __forceinline__ uint32_t fp_from_mont(uint32_t a) { return fp_mul(a, 1u); }
+__device__ __forceinline__ uint32_t fp_pow(uint32_t a, uint64_t e) {
+    uint32_t r = R1;
+    while (e) { if (e & 1) r = fp_mul(r, a); a = fp_mul(a, a); e >>= 1; }
+    return r;
+}
+
+struct Fp4 { uint32_t c[4]; };
+
+__device__ __forceinline__ Fp4 fp4_zero() { return Fp4{{0u, 0u, 0u, 0u}}; }
+__device__ __forceinline__ Fp4 fp4_one() { return Fp4{{R1, 0u, 0u, 0u}}; }
+__device__ __forceinline__ Fp4 fp4_add(const Fp4& a, const Fp4& b) {
+    return Fp4{{fp_add(a.c[0], b.c[0]), fp_add(a.c[1], b.c[1]), fp_add(a.c[2], b.c[2]), fp_add(a.c[3], b.c[3])}};
+}
+__device__ __forceinline__ Fp4 fp4_sub(const Fp4& a, const Fp4& b) {
+    return Fp4{{fp_sub(a.c[0], b.c[0]), fp_sub(a.c[1], b.c[1]), fp_sub(a.c[2], b.c[2]), fp_sub(a.c[3], b.c[3])}};
+}
+__device__ __forceinline__ Fp4 fp4_mul_fp(const Fp4& a, uint32_t b) {
+    return Fp4{{fp_mul(a.c[0], b), fp_mul(a.c[1], b), fp_mul(a.c[2], b), fp_mul(a.c[3], b)}};
+}
+// acc += a * b (b in Fp)
+__device__ __forceinline__ void fp4_fma_fp(Fp4& acc, const Fp4& a, uint32_t b) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) acc.c[i] = fp_add(acc.c[i], fp_mul(a.c[i], b));
+}
+// ExtElem multiply over X^4 = -11 (same formula as risc0-zkp field/baby_bear.rs ExtElem::mul)
+__device__ __forceinline__ Fp4 fp4_mul(const Fp4& a, const Fp4& b) {
+    Fp4 r;
+    r.c[0] = fp_add(fp_mul(a.c[0], b.c[0]),
+                    fp_mul(NBETA_M, fp_add(fp_add(fp_mul(a.c[1], b.c[3]), fp_mul(a.c[2], b.c[2])), fp_mul(a.c[3], b.c[1]))));
+    r.c[1] = fp_add(fp_add(fp_mul(a.c[0], b.c[1]), fp_mul(a.c[1], b.c[0])),
+                    fp_mul(NBETA_M, fp_add(fp_mul(a.c[2], b.c[3]), fp_mul(a.c[3], b.c[2]))));
+    r.c[2] = fp_add(fp_add(fp_add(fp_mul(a.c[0], b.c[2]), fp_mul(a.c[1], b.c[1])), fp_mul(a.c[2], b.c[0])),
+                    fp_mul(NBETA_M, fp_mul(a.c[3], b.c[3])));
+    r.c[3] = fp_add(fp_add(fp_mul(a.c[0], b.c[3]), fp_mul(a.c[1], b.c[2])),
+                    fp_add(fp_mul(a.c[2], b.c[1]), fp_mul(a.c[3], b.c[0])));
+    return r;
+}
+__device__ __forceinline__ Fp4 fp4_pow(Fp4 a, uint64_t e) {
+    Fp4 r = fp4_one();
+    while (e) { if (e & 1) r = fp4_mul(r, a); a = fp4_mul(a, a); e >>= 1; }
+    return r;
+}
+
+__device__ __forceinline__ uint32_t bitrev(uint32_t x, uint32_t bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
+
+}  // namespace b200

@@ -1,0 +1,113 @@
+// Internal (non-ABI) declarations shared by the translation units of libb200zkp.so.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+constexpr int MAX_LG = 24;          // largest transform size 2^24
+constexpr int QUERIES = 50;
+constexpr int INV_RATE_LG = 2;      // blow-up 4
+constexpr int FRI_FOLD = 16;
+constexpr int FRI_MIN_DEGREE = 256;
+constexpr int CHECK_COLS = 16;
+constexpr int GLOBALS = 16;
+
+// ---- per-device read-only tables (tables.cpp) --------------------------------------------------------
+struct DeviceTables {
+    int device;
+    // stage twiddles, compact per-level layout: tw[2^(l-1) + i] = w_{2^l}^i, i < 2^(l-1), l <= 12
+    uint32_t* tw_fwd;      // 4096 entries
+    uint32_t* tw_inv;      // 4096 entries
+    // six-step inter-pass twiddle decomposition for transform size 2^m:  w_{2^m}^e = lo[e & (2^h-1)] * hi[e >> h], h = ceil(m/2)
+    uint32_t* pow_fwd[MAX_LG + 1];      // lo (2^h) followed by hi (2^(m-h))
+    uint32_t* pow_inv[MAX_LG + 1];      // inverse roots; hi table pre-scaled by 2^-m (iNTT normalisation)
+    // zk_shift: 3^d = p3lo[d & 4095] * p3hi[d >> 12]
+    uint32_t* p3lo;
+    uint32_t* p3hi;
+    uint32_t rou_fwd[28], rou_rev[28];  // host copies, Montgomery
+};
+const DeviceTables* get_tables(int device);   // lazily built, thread-safe; nullptr + error string on failure
+const char* last_error();
+void set_error(const char* fmt, ...);
+
+// host-side field helpers (tables.cpp)
+uint32_t h_mul(uint32_t a, uint32_t b);
+uint32_t h_add(uint32_t a, uint32_t b);
+uint32_t h_sub(uint32_t a, uint32_t b);
+uint32_t h_pow(uint32_t a, uint64_t e);
+uint32_t h_inv(uint32_t a);
+uint32_t h_to_mont(uint32_t x);
+uint32_t h_from_mont(uint32_t a);
+
+// ---- NTT (ntt.cu) ------------------------------------------------------------------------------------
+// K1: `count` in-place iNTTs of size 2^lg_n, natural-order evaluations -> bit-reversed coefficients, scaled by 2^-lg_n.
+cudaError_t launch_batch_intt(const DeviceTables* T, uint32_t* d_io, uint32_t lg_n, uint32_t count, cudaStream_t s);
+// forward, bit-reversed coefficients -> natural-order evaluations, in place
+cudaError_t launch_batch_ntt(const DeviceTables* T, uint32_t* d_io, uint32_t lg_n, uint32_t count, cudaStream_t s);
+// K3: out (count x 2^(lg_n+lg_blowup)) = NTT of the zero-padded (== replicated, levels skipped) coefficients
+cudaError_t launch_batch_expand_ntt(const DeviceTables* T, uint32_t* d_out, const uint32_t* d_in, uint32_t lg_n,
+                                    uint32_t lg_blowup, uint32_t count, cudaStream_t s);
+// K2: coefficient of x^d *= 3^d (slot j holds degree bitrev(j))
+cudaError_t launch_zk_shift(const DeviceTables* T, uint32_t* d_io, uint32_t lg_n, uint32_t count, cudaStream_t s);
+cudaError_t launch_bit_reverse(uint32_t* d_io, uint32_t lg_n, uint32_t count, cudaStream_t s);
+
+// ---- Poseidon2 / Merkle / transcript (hash.cu) -------------------------------------------------------
+// K4: leaf j = sponge(matrix[c*col_stride + j], c < cols); out = rows x 8 words
+cudaError_t launch_poseidon2_rows(uint32_t* d_out, const uint32_t* d_matrix, uint32_t rows, uint32_t cols,
+                                  size_t col_stride, cudaStream_t s);
+// K5: nodes[2*rows*8]; leaves in nodes[rows..2rows) -> fills nodes[1..rows)
+cudaError_t launch_poseidon2_fold_tree(uint32_t* d_nodes, uint32_t lg_rows, cudaStream_t s);
+// single-layer fold: out[i] = hash_pair(in[2i], in[2i+1]), i < n_out
+cudaError_t launch_poseidon2_fold(uint32_t* d_out, const uint32_t* d_in, uint32_t n_out, cudaStream_t s);
+
+struct Transcript { uint32_t cells[24]; uint32_t pool_used; uint32_t pad[7]; };
+cudaError_t launch_iop_init(Transcript* t, cudaStream_t s);
+cudaError_t launch_iop_commit(Transcript* t, const uint32_t* d_digest8, cudaStream_t s);
+// hash_elem_slice(d_elems[0..count)) then rng.mix(digest); optional copy of the digest to d_digest_out
+cudaError_t launch_iop_commit_elems(Transcript* t, const uint32_t* d_elems, uint32_t count, uint32_t* d_digest_out, cudaStream_t s);
+cudaError_t launch_iop_draw_ext(Transcript* t, uint32_t* d_out, uint32_t n_ext, cudaStream_t s);
+cudaError_t launch_iop_draw_bits(Transcript* t, uint32_t* d_out, uint32_t n, uint32_t bits, cudaStream_t s);
+cudaError_t launch_hash_elems(uint32_t* d_digest_out, const uint32_t* d_elems, uint32_t count, cudaStream_t s);
+cudaError_t launch_hash_pair_one(uint32_t* d_out8, const uint32_t* d_a8, const uint32_t* d_b8, cudaStream_t s);
+
+// ---- STARK plumbing (stark.cu) -----------------------------------------------------------------------
+cudaError_t launch_gen_trace(uint32_t* d_out, uint64_t seed, const uint32_t* d_seed_words, uint64_t count, cudaStream_t s);
+cudaError_t launch_set_globals(uint32_t* d_seal, uint32_t po2, uint32_t w_code, uint32_t w_data, uint32_t w_accum, uint32_t kind, uint64_t seed, int hash_seed, cudaStream_t s);
+cudaError_t launch_accumulate(uint32_t* d_acc_io, uint32_t rows, uint32_t w_accum, const uint32_t* d_mix, cudaStream_t s);
+cudaError_t launch_powers(uint32_t* d_out, const uint32_t* d_base, uint32_t count, cudaStream_t s);   // out[k] = base^k (Fp4)
+cudaError_t launch_eval_check(uint32_t* d_planes, const uint32_t* d_evals, uint32_t lg_domain, uint32_t w_code,
+                              uint32_t w_data, uint32_t w_accum, const uint32_t* d_pmix, cudaStream_t s);
+// K6
+cudaError_t launch_fri_fold(uint32_t* d_out, const uint32_t* d_in, uint32_t in_size, const uint32_t* d_mix, cudaStream_t s);
+// K7: evaluate `count` bit-reversed coefficient columns (size 2^lg_n) at Fp4 point d_x; cols [b0,b1) also at d_xb (may be null).
+cudaError_t launch_evaluate(uint32_t* d_out_a, uint32_t* d_out_b, const uint32_t* d_coeffs, uint32_t lg_n, uint32_t count,
+                            const uint32_t* d_x, const uint32_t* d_xb, uint32_t b0, uint32_t b1, uint32_t* d_scratch,
+                            cudaStream_t s);
+size_t evaluate_scratch_words(uint32_t lg_n, uint32_t count);
+// derive the DEEP points from z: pts = [z, z * w_N^-1, z^4] (3 Fp4)
+cudaError_t launch_deep_points(uint32_t* d_pts, const uint32_t* d_z, uint32_t rou_rev_n, cudaStream_t s);
+// K8: DEEP combination + division + sum -> F planes (4 x N, bit-reversed)
+struct DeepArgs {
+    const uint32_t* coeffs;        // W columns x N (code, data, accum)
+    const uint32_t* check_coeffs;  // 16 columns x N
+    const uint32_t* u;             // T Fp4 tap evaluations
+    const uint32_t* mix_pows;      // T Fp4 powers of the DEEP mix
+    const uint32_t* pts;           // 3 Fp4 points
+    uint32_t* combos;              // scratch: 3 x N Fp4 (AoS, natural degree order)
+    uint32_t* chunk_vals;          // scratch: 3 x nchunks Fp4
+    uint32_t* chunk_carry;         // scratch: 3 x nchunks Fp4
+    uint32_t* f_planes;            // out: 4 x N
+    uint32_t lg_n, W, w_accum;
+};
+cudaError_t launch_deep(const DeepArgs& a, cudaStream_t s);
+// K9: gather one Merkle opening per (query, tree) into the seal
+struct GatherTree {
+    const uint32_t* matrix; const uint32_t* nodes; uint32_t rows, cols, top_size; uint32_t seal_off;  // offset within a query record
+    uint32_t pos_shift_mod;   // rows for "pos % rows" chaining (FRI) or 0 for trace groups (use pos as is)
+};
+cudaError_t launch_gather_queries(uint32_t* d_seal, uint32_t query_base, uint32_t query_words, const uint32_t* d_pos,
+                                  const GatherTree* d_trees, uint32_t n_trees, cudaStream_t s);
+
+}  // namespace b200

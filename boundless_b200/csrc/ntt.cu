@@ -1,0 +1,318 @@
+// Batched NTT / iNTT / expand+NTT / zk_shift over BabyBear for sm_100a (kernel 1 of the hot path).
+//
+// Replaces risc0-sys 1.5.0's sppark_batch_iNTT / sppark_batch_NTT / sppark_batch_expand / sppark_batch_zk_shift
+// (un-vendored), reached from
+// /root/reference/prover/crates/workflow/src/tasks/prove.rs:44-52 (prove_segment) and :96-104 (lift).
+// Conventions are the reference's: iNTT maps natural-order evaluations to BIT-REVERSED coefficients scaled
+// by 1/n; the forward transform maps bit-reversed coefficients to natural-order evaluations; `expand` is the
+// x4 replicate that equals zero padding in bit-reversed order, so the first lg_blowup levels are skipped.
+//
+// Design (B200): a size-2^m transform is two HBM passes (six-step): N = N1*N2.
+//   iNTT : pass A  strided tile [N1 rows][TW cols] in shared memory, DIF along rows, then the inter-pass
+//                  twiddle w^-(i0*bitrev(r)) (and the 1/N scale, folded into the twiddle table), in place;
+//          pass B  contiguous rows of N2, DIF, in place.
+//   fwd  : pass 1  contiguous row of N2 coefficients -> replicated x4 in shared memory -> DIT (levels above
+//                  the blow-up) -> inter-pass twiddle -> written as a row of 4*N2;
+//          pass 2  strided tile, DIT along rows, in place.
+// Every pass moves each element HBM->smem->HBM once with >=32-byte runs; butterflies are radix-16 register
+// stages (4 levels per shared-memory round trip); stage twiddles come from a compact per-level table staged
+// in shared memory, inter-pass twiddles from a two-table decomposition w^e = lo[e & mask] * hi[e >> h].
+#include "internal.h"
+#include "field.cuh"
+
+namespace b200 {
+
+struct AddrStrided {
+    uint32_t lgTW, t;
+    __device__ __forceinline__ uint32_t operator()(uint32_t pos) const { return (pos << lgTW) + t; }
+};
+struct AddrContig {
+    uint32_t base;
+    // one pad word per 16 keeps the radix-16 gathers (stride q < 32) free of bank conflicts
+    __device__ __forceinline__ uint32_t operator()(uint32_t pos) const { return base + pos + (pos >> 4); }
+};
+
+// One radix-2^K register stage: gathers the 2^K elements base + j*q of the block of size 2^lb that contains them,
+// runs K butterfly levels in registers and scatters them back.  tw is the compact table tw[2^(l-1)+i] = w_{2^l}^i.
+template <int K, bool DIF, typename ADDR>
+__device__ __forceinline__ void ntt_stage(uint32_t* s, const uint32_t* __restrict__ tw, uint32_t lb, uint32_t gidx, ADDR addr) {
+    constexpr int R = 1 << K;
+    const uint32_t q = (1u << lb) >> K;
+    const uint32_t b = gidx >> (lb - K), o = gidx & (q - 1);
+    const uint32_t base = (b << lb) + o;
+    uint32_t x[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) x[j] = s[addr(base + j * q)];
+#pragma unroll
+    for (int ll = 0; ll < K; ll++) {
+        const int l = DIF ? ll : (K - 1 - ll);
+        const int half = R >> (l + 1);
+        const uint32_t twbase = ((1u << lb) >> (l + 1)) + o;
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            if ((j & half) == 0) {
+                const uint32_t w = tw[twbase + (j & (half - 1)) * q];
+                const uint32_t a = x[j], bb = x[j + half];
+                if (DIF) {
+                    x[j] = fp_add(a, bb);
+                    x[j + half] = fp_mul(fp_sub(a, bb), w);
+                } else {
+                    const uint32_t t = fp_mul(bb, w);
+                    x[j] = fp_add(a, t);
+                    x[j + half] = fp_sub(a, t);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < R; j++) s[addr(base + j * q)] = x[j];
+}
+
+template <bool DIF, typename ADDR>
+__device__ __forceinline__ void ntt_stage_k(int K, uint32_t* s, const uint32_t* tw, uint32_t lb, uint32_t gidx, ADDR addr) {
+    switch (K) {
+        case 4: ntt_stage<4, DIF>(s, tw, lb, gidx, addr); break;
+        case 3: ntt_stage<3, DIF>(s, tw, lb, gidx, addr); break;
+        case 2: ntt_stage<2, DIF>(s, tw, lb, gidx, addr); break;
+        default: ntt_stage<1, DIF>(s, tw, lb, gidx, addr); break;
+    }
+}
+
+struct PowTab {          // w^e = lo[e & mask] * hi[e >> h]
+    const uint32_t* lo; const uint32_t* hi; uint32_t h, mask;
+    __device__ __forceinline__ uint32_t operator()(uint32_t e) const { return fp_mul(lo[e & mask], hi[e >> h]); }
+};
+
+// ---- strided pass: tile [L][TW], FFT along rows -------------------------------------------------------
+// data element (row r, col c) of polynomial p lives at data[p*poly_stride + r*row_stride + c].
+template <bool DIF>
+__global__ void __launch_bounds__(512) k_ntt_strided(uint32_t* __restrict__ data, uint32_t logL, uint32_t lgTW, uint32_t row_stride,
+                                                     uint32_t tiles_per_poly, size_t poly_stride,
+                                                     const uint32_t* __restrict__ tw_g, const uint32_t* __restrict__ pow_g,
+                                                     uint32_t lg_m) {
+    extern __shared__ uint32_t smem[];
+    const uint32_t L = 1u << logL, TW = 1u << lgTW;
+    uint32_t* tile = smem;                  // L * TW
+    uint32_t* tw = tile + (L << lgTW);      // L
+    uint32_t* pw = tw + L;                  // 2^h + 2^(m-h) when pow_g
+    const uint32_t tid = threadIdx.x, nth = blockDim.x;
+    const uint32_t poly = blockIdx.x / tiles_per_poly, tcol = blockIdx.x % tiles_per_poly;
+    uint32_t* g = data + (size_t)poly * poly_stride + ((size_t)tcol << lgTW);
+
+    for (uint32_t i = tid; i < L; i += nth) tw[i] = tw_g[i];
+    const uint32_t h = (lg_m + 1) / 2;
+    if (pow_g) { const uint32_t n = (1u << h) + (1u << (lg_m - h)); for (uint32_t i = tid; i < n; i += nth) pw[i] = pow_g[i]; }
+    for (uint32_t i = tid; i < (L << lgTW); i += nth) tile[i] = g[(size_t)(i >> lgTW) * row_stride + (i & (TW - 1))];
+    __syncthreads();
+
+    if (DIF) {
+        uint32_t lb = logL;
+        while (lb > 0) {
+            const int K = lb >= 4 ? 4 : (int)lb;
+            const uint32_t total = (L >> K) << lgTW;
+            for (uint32_t w = tid; w < total; w += nth) ntt_stage_k<true>(K, tile, tw, lb, w >> lgTW, AddrStrided{lgTW, w & (TW - 1)});
+            __syncthreads();
+            lb -= K;
+        }
+    } else {
+        uint32_t done = 0;
+        while (done < logL) {
+            const int K = (logL - done) >= 4 ? 4 : (int)(logL - done);
+            const uint32_t lb = done + K;
+            const uint32_t total = (L >> K) << lgTW;
+            for (uint32_t w = tid; w < total; w += nth) ntt_stage_k<false>(K, tile, tw, lb, w >> lgTW, AddrStrided{lgTW, w & (TW - 1)});
+            __syncthreads();
+            done += K;
+        }
+    }
+    if (pow_g) {
+        PowTab pt{pw, pw + (1u << h), h, (1u << h) - 1};
+        const uint32_t mmask = (lg_m >= 32) ? 0xffffffffu : ((1u << lg_m) - 1);
+        for (uint32_t i = tid; i < (L << lgTW); i += nth) {
+            const uint32_t r = i >> lgTW, c = (tcol << lgTW) + (i & (TW - 1));
+            const uint32_t e = (c * bitrev(r, logL)) & mmask;
+            g[(size_t)r * row_stride + (i & (TW - 1))] = fp_mul(tile[i], pt(e));
+        }
+    } else {
+        for (uint32_t i = tid; i < (L << lgTW); i += nth) g[(size_t)(i >> lgTW) * row_stride + (i & (TW - 1))] = tile[i];
+    }
+}
+
+// ---- contiguous pass: rows of Lc elements, FFT along the row -----------------------------------------
+// input row (length Lc >> lg_e) is replicated x 2^lg_e into shared memory (forward/expand) or copied (lg_e = 0).
+template <bool DIF>
+__global__ void __launch_bounds__(256) k_ntt_contig(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, uint32_t logLc,
+                                                    uint32_t lg_e, uint32_t rows_per_cta, uint32_t rows_per_poly, uint32_t total_rows,
+                                                    size_t in_poly_stride, size_t out_poly_stride,
+                                                    const uint32_t* __restrict__ tw_g, const uint32_t* __restrict__ pow_g,
+                                                    uint32_t lg_m, uint32_t lg_rows, uint32_t scale) {
+    extern __shared__ uint32_t smem[];
+    const uint32_t Lc = 1u << logLc, Lin = Lc >> lg_e;
+    const uint32_t rowpad = Lc + (Lc >> 4);
+    uint32_t* tile = smem;                              // rows_per_cta * rowpad
+    uint32_t* tw = tile + rows_per_cta * rowpad;        // Lc
+    uint32_t* pw = tw + Lc;
+    const uint32_t tid = threadIdx.x, nth = blockDim.x;
+    const uint32_t row0 = blockIdx.x * rows_per_cta;
+
+    for (uint32_t i = tid; i < Lc; i += nth) tw[i] = tw_g[i];
+    const uint32_t h = (lg_m + 1) / 2;
+    if (pow_g) { const uint32_t n = (1u << h) + (1u << (lg_m - h)); for (uint32_t i = tid; i < n; i += nth) pw[i] = pow_g[i]; }
+    for (uint32_t i = tid; i < rows_per_cta * Lin; i += nth) {
+        const uint32_t rr = i / Lin, k = i - rr * Lin, R = row0 + rr;
+        if (R < total_rows) {
+            const uint32_t poly = R / rows_per_poly, rho = R - poly * rows_per_poly;
+            const uint32_t v = in[(size_t)poly * in_poly_stride + (size_t)rho * Lin + k];
+            AddrContig ad{rr * rowpad};
+            for (uint32_t e = 0; e < (1u << lg_e); e++) tile[ad((k << lg_e) + e)] = v;
+        }
+    }
+    __syncthreads();
+
+    const uint32_t nlev = logLc - lg_e;
+    if (DIF) {
+        uint32_t lb = logLc;        // lg_e == 0 for DIF
+        while (lb > 0) {
+            const int K = lb >= 4 ? 4 : (int)lb;
+            const uint32_t per_row = Lc >> K, total = rows_per_cta * per_row;
+            for (uint32_t w = tid; w < total; w += nth) { const uint32_t rr = w / per_row; ntt_stage_k<true>(K, tile, tw, lb, w - rr * per_row, AddrContig{rr * rowpad}); }
+            __syncthreads();
+            lb -= K;
+        }
+    } else {
+        uint32_t done = 0;
+        while (done < nlev) {
+            const int K = (nlev - done) >= 4 ? 4 : (int)(nlev - done);
+            const uint32_t lb = lg_e + done + K;
+            const uint32_t per_row = Lc >> K, total = rows_per_cta * per_row;
+            for (uint32_t w = tid; w < total; w += nth) { const uint32_t rr = w / per_row; ntt_stage_k<false>(K, tile, tw, lb, w - rr * per_row, AddrContig{rr * rowpad}); }
+            __syncthreads();
+            done += K;
+        }
+    }
+    PowTab pt{pw, pw + (1u << h), h, (1u << h) - 1};
+    const uint32_t mmask = (1u << lg_m) - 1;
+    for (uint32_t i = tid; i < rows_per_cta * Lc; i += nth) {
+        const uint32_t rr = i >> logLc, k = i & (Lc - 1), R = row0 + rr;
+        if (R < total_rows) {
+            const uint32_t poly = R / rows_per_poly, rho = R - poly * rows_per_poly;
+            uint32_t v = tile[AddrContig{rr * rowpad}(k)];
+            if (pow_g) v = fp_mul(v, pt((k * bitrev(rho, lg_rows)) & mmask));
+            else if (scale) v = fp_mul(v, scale);
+            out[(size_t)poly * out_poly_stride + (size_t)rho * Lc + k] = v;
+        }
+    }
+}
+
+__global__ void k_zk_shift(uint32_t* __restrict__ io, uint32_t lg_n, size_t total, const uint32_t* __restrict__ p3lo,
+                           const uint32_t* __restrict__ p3hi) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const uint32_t d = bitrev((uint32_t)(i & ((1u << lg_n) - 1)), lg_n);
+    io[i] = fp_mul(io[i], fp_mul(p3lo[d & 4095], p3hi[d >> 12]));
+}
+
+__global__ void k_bit_reverse(uint32_t* __restrict__ io, uint32_t lg_n, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const uint32_t j = (uint32_t)(i & ((1u << lg_n) - 1));
+    const uint32_t r = bitrev(j, lg_n);
+    if (j < r) { size_t b = i - j; uint32_t t = io[b + j]; io[b + j] = io[b + r]; io[b + r] = t; }
+}
+
+// ---- host launchers ------------------------------------------------------------------------------------
+static uint32_t strided_lgTW(uint32_t logL) {
+    // target 64 KB tiles, at least 8 columns (32-byte runs), at most 32
+    uint32_t lg = logL >= 14 ? 3 : (14 - logL);
+    if (lg > 5) lg = 5;
+    if (lg < 3) lg = 3;
+    return lg;
+}
+static uint32_t split_n1(uint32_t lg) { uint32_t n1 = lg / 2; return n1 > 11 ? 11 : n1; }
+
+template <bool DIF>
+static cudaError_t run_strided(const DeviceTables* T, uint32_t* d, uint32_t logL, uint32_t row_stride, uint32_t ncols, uint32_t count,
+                               size_t poly_stride, const uint32_t* pow_g, uint32_t lg_m, cudaStream_t s) {
+    uint32_t lgTW = strided_lgTW(logL);
+    while ((1u << lgTW) > ncols) lgTW--;
+    const uint32_t tiles_per_poly = ncols >> lgTW;
+    const uint32_t h = (lg_m + 1) / 2;
+    size_t smem = ((size_t)(1u << logL) << lgTW) * 4 + ((size_t)4 << logL) + (pow_g ? ((size_t)4 << h) + ((size_t)4 << (lg_m - h)) : 0);
+    auto kern = k_ntt_strided<DIF>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<tiles_per_poly * count, 512, smem, s>>>(d, logL, lgTW, row_stride, tiles_per_poly, poly_stride,
+                                                    DIF ? T->tw_inv : T->tw_fwd, pow_g, lg_m);
+    return cudaGetLastError();
+}
+
+template <bool DIF>
+static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32_t* in, uint32_t logLc, uint32_t lg_e, uint32_t rows_per_poly,
+                              uint32_t count, size_t in_stride, size_t out_stride, const uint32_t* pow_g, uint32_t lg_m,
+                              uint32_t lg_rows, uint32_t scale, cudaStream_t s) {
+    uint32_t rpc = logLc >= 12 ? 1 : (1u << (12 - logLc));
+    const uint64_t total_rows = (uint64_t)rows_per_poly * count;
+    if (rpc > total_rows) rpc = (uint32_t)total_rows;
+    const uint32_t h = (lg_m + 1) / 2;
+    const uint32_t Lc = 1u << logLc;
+    size_t smem = (size_t)rpc * (Lc + (Lc >> 4)) * 4 + (size_t)Lc * 4 + (pow_g ? ((size_t)4 << h) + ((size_t)4 << (lg_m - h)) : 0);
+    auto kern = k_ntt_contig<DIF>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint32_t grid = (uint32_t)((total_rows + rpc - 1) / rpc);
+    kern<<<grid, 256, smem, s>>>(out, in, logLc, lg_e, rpc, rows_per_poly, (uint32_t)total_rows, in_stride, out_stride,
+                                 DIF ? T->tw_inv : T->tw_fwd, pow_g, lg_m, lg_rows, scale);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_batch_intt(const DeviceTables* T, uint32_t* d_io, uint32_t lg_n, uint32_t count, cudaStream_t s) {
+    if (lg_n == 0 || count == 0) return cudaSuccess;
+    if (lg_n > MAX_LG) return cudaErrorInvalidValue;
+    const size_t N = (size_t)1 << lg_n;
+    if (lg_n <= 12) {
+        const uint32_t scale = h_inv(h_to_mont((uint32_t)N));
+        return run_contig<true>(T, d_io, d_io, lg_n, 0, 1, count, N, N, nullptr, 0, 0, scale, s);
+    }
+    const uint32_t n1 = split_n1(lg_n), n2 = lg_n - n1;
+    // pass A: DIF over i1 (rows of stride N2) + twiddle (1/N folded into the table)
+    cudaError_t e = run_strided<true>(T, d_io, n1, 1u << n2, 1u << n2, count, N, T->pow_inv[lg_n], lg_n, s);
+    if (e != cudaSuccess) return e;
+    // pass B: DIF over each contiguous row of N2
+    return run_contig<true>(T, d_io, d_io, n2, 0, 1u << n1, count, N, N, nullptr, 0, 0, 0, s);
+}
+
+cudaError_t launch_batch_expand_ntt(const DeviceTables* T, uint32_t* d_out, const uint32_t* d_in, uint32_t lg_n, uint32_t lg_e,
+                                    uint32_t count, cudaStream_t s) {
+    if (count == 0) return cudaSuccess;
+    const uint32_t lg_m = lg_n + lg_e;
+    if (lg_m > MAX_LG + 2 || lg_m == 0) return cudaErrorInvalidValue;
+    const size_t N = (size_t)1 << lg_n, M = (size_t)1 << lg_m;
+    if (lg_m <= 13) return run_contig<false>(T, d_out, d_in, lg_m, lg_e, 1, count, N, M, nullptr, 0, 0, 0, s);
+    if (lg_m > MAX_LG) return cudaErrorInvalidValue;
+    const uint32_t n1 = split_n1(lg_n), n2 = lg_n - n1;
+    // pass 1: row rho (N2 coefficients) -> 2^lg_e * N2 values, times w_M^(i0 * bitrev(rho))
+    cudaError_t e = run_contig<false>(T, d_out, d_in, n2 + lg_e, lg_e, 1u << n1, count, N, M, T->pow_fwd[lg_m], lg_m, n1, 0, s);
+    if (e != cudaSuccess) return e;
+    // pass 2: DIT over rho (rows of stride 2^lg_e * N2)
+    return run_strided<false>(T, d_out, n1, 1u << (n2 + lg_e), 1u << (n2 + lg_e), count, M, nullptr, 0, s);
+}
+
+cudaError_t launch_batch_ntt(const DeviceTables* T, uint32_t* d_io, uint32_t lg_n, uint32_t count, cudaStream_t s) {
+    return launch_batch_expand_ntt(T, d_io, d_io, lg_n, 0, count, s);
+}
+
+cudaError_t launch_zk_shift(const DeviceTables* T, uint32_t* d_io, uint32_t lg_n, uint32_t count, cudaStream_t s) {
+    const size_t total = (size_t)count << lg_n;
+    if (total == 0) return cudaSuccess;
+    k_zk_shift<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_io, lg_n, total, T->p3lo, T->p3hi);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bit_reverse(uint32_t* d_io, uint32_t lg_n, uint32_t count, cudaStream_t s) {
+    const size_t total = (size_t)count << lg_n;
+    if (total == 0) return cudaSuccess;
+    k_bit_reverse<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_io, lg_n, total);
+    return cudaGetLastError();
+}
+
+}  // namespace b200

@@ -1,0 +1,95 @@
+// Poseidon2 permutation over BabyBear, t=24 (rate 16, capacity 8), x^7, 8 full + 21 partial rounds.
+//
+// Device counterpart of risc0-sys' `sppark_poseidon2_rows` / `sppark_poseidon2_fold` inner permutation
+// (un-vendored; SURVEY.md 2.1 kernel 2, Appendix A "Poseidon2"); reached from
+// /root/reference/prover/crates/workflow/src/tasks/prove.rs:44-52 via ProverServer::prove_segment.
+//
+// One thread owns one 24-cell state in registers.  The kernel is INT32-pipe bound (1356 Montgomery
+// multiplications per permutation), so the code is organised around instruction count:
+//   * add/sub are IADD + VIADDMNMX (field.cuh);
+//   * the internal layer s + d_i*c_i folds the "+ s" into the 64-bit IMAD.WIDE accumulator, so a cell
+//     update costs one Montgomery multiply and no separate modular add;
+//   * round constants / diagonal come from __constant__ (uniform across the warp -> c[bank][ofs] operands).
+#pragma once
+#include "field.cuh"
+#include "constants.inc"
+
+namespace b200 {
+
+static __constant__ uint32_t c_rc[213] = B200_P2_RC_INIT;      // Montgomery form
+static __constant__ uint32_t c_diag[24] = B200_P2_DIAG_INIT;   // Montgomery form
+
+__device__ __forceinline__ uint32_t p2_sbox(uint32_t x) {
+    uint32_t x2 = fp_mul(x, x);
+    uint32_t x3 = fp_mul(x2, x);
+    uint32_t x4 = fp_mul(x2, x2);
+    return fp_mul(x3, x4);
+}
+
+// external linear layer: circ(2*M4, M4, ..., M4), M4 = [[5,7,1,3],[4,6,1,1],[1,3,5,7],[1,1,4,6]]
+__device__ __forceinline__ void p2_m_ext(uint32_t (&c)[24]) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        uint32_t x0 = c[4 * k], x1 = c[4 * k + 1], x2 = c[4 * k + 2], x3 = c[4 * k + 3];
+        uint32_t t0 = fp_add(x0, x1), t1 = fp_add(x2, x3);
+        uint32_t t2 = fp_add(fp_dbl(x1), t1), t3 = fp_add(fp_dbl(x3), t0);
+        uint32_t t4 = fp_add(fp_dbl(fp_dbl(t1)), t3), t5 = fp_add(fp_dbl(fp_dbl(t0)), t2);
+        c[4 * k] = fp_add(t3, t5);
+        c[4 * k + 1] = t5;
+        c[4 * k + 2] = fp_add(t2, t4);
+        c[4 * k + 3] = t4;
+    }
+    uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        s0 = fp_add(s0, c[4 * k]); s1 = fp_add(s1, c[4 * k + 1]);
+        s2 = fp_add(s2, c[4 * k + 2]); s3 = fp_add(s3, c[4 * k + 3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        c[4 * k] = fp_add(c[4 * k], s0); c[4 * k + 1] = fp_add(c[4 * k + 1], s1);
+        c[4 * k + 2] = fp_add(c[4 * k + 2], s2); c[4 * k + 3] = fp_add(c[4 * k + 3], s3);
+    }
+}
+
+// internal linear layer: c_i <- s + diag_i * c_i, s = sum c.
+// "+ s" rides in the IMAD.WIDE accumulator: X == s*2^32 (mod p) with hi(X) < p/2, so d*c + X < p*2^32.
+__device__ __forceinline__ void p2_m_int(uint32_t (&c)[24]) {
+    uint32_t a0 = fp_add(c[0], c[1]), a1 = fp_add(c[2], c[3]), a2 = fp_add(c[4], c[5]), a3 = fp_add(c[6], c[7]);
+    uint32_t a4 = fp_add(c[8], c[9]), a5 = fp_add(c[10], c[11]), a6 = fp_add(c[12], c[13]), a7 = fp_add(c[14], c[15]);
+    uint32_t a8 = fp_add(c[16], c[17]), a9 = fp_add(c[18], c[19]), a10 = fp_add(c[20], c[21]), a11 = fp_add(c[22], c[23]);
+    a0 = fp_add(a0, a1); a2 = fp_add(a2, a3); a4 = fp_add(a4, a5); a6 = fp_add(a6, a7); a8 = fp_add(a8, a9); a10 = fp_add(a10, a11);
+    a0 = fp_add(a0, a2); a4 = fp_add(a4, a6); a8 = fp_add(a8, a10);
+    uint32_t s = fp_add(fp_add(a0, a4), a8);
+    // X = s<<32 if s < (p+1)/2 else ((2s-p)<<31) = {hi: s-(p+1)/2, lo: 0x80000000}
+    constexpr uint32_t HALF = (P + 1) / 2;
+    bool big = s >= HALF;
+    uint32_t xhi = big ? s - HALF : s;
+    uint32_t xlo = big ? 0x80000000u : 0u;
+    uint64_t X = ((uint64_t)xhi << 32) | xlo;
+#pragma unroll
+    for (int i = 0; i < 24; i++) c[i] = fp_mul_acc(c_diag[i], c[i], X);
+}
+
+__device__ __forceinline__ void p2_permute(uint32_t (&c)[24]) {
+    p2_m_ext(c);
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 24; i++) c[i] = p2_sbox(fp_add(c[i], c_rc[24 * r + i]));
+        p2_m_ext(c);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 21; r++) {
+        c[0] = p2_sbox(fp_add(c[0], c_rc[96 + r]));
+        p2_m_int(c);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 24; i++) c[i] = p2_sbox(fp_add(c[i], c_rc[117 + 24 * r + i]));
+        p2_m_ext(c);
+    }
+}
+
+}  // namespace b200

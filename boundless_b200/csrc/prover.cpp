@@ -1,0 +1,399 @@
+// Host pipeline behind the ProverServer operator boundary: prove_segment / lift / join as ONE stream of kernel
+// launches with no host round trip (transcript, challenges and query positions live in device memory).
+//
+// Mirrors the call sequence of risc0-zkp 3.0.3 prove/prover.rs + prove/fri.rs + prove/merkle.rs (un-vendored;
+// SURVEY.md Appendix A "Prover loop") as invoked through ProverServer::prove_segment / lift / join at
+// /root/reference/prover/crates/workflow/src/tasks/prove.rs:44-52, :96-104 and tasks/join.rs:52-56.
+// The circuit is synthetic (DESIGN.md "Protocol"): witgen and eval_check are stand-ins, everything between them
+// (K1-K9) is the real work at the real shapes.
+#include "../../include/b200zkp.h"
+#include "internal.h"
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace b200 {
+
+static unsigned ilog2(size_t x) { unsigned r = 0; while (((size_t)1 << r) < x) r++; return r; }
+
+struct MerkleShape {
+    uint32_t rows, cols, layers, top_layer, top_size;
+    MerkleShape(uint32_t r, uint32_t c) : rows(r), cols(c) {
+        layers = ilog2(r); top_layer = layers < 5 ? layers : 5; top_size = 1u << top_layer;
+    }
+    uint32_t proof_words() const { return cols + (layers - top_layer) * 8; }
+};
+
+static unsigned fri_rounds(unsigned po2, size_t* final_size) {
+    size_t size = (size_t)1 << po2; unsigned r = 0;
+    while (size > (size_t)FRI_MIN_DEGREE) { size /= FRI_FOLD; r++; }
+    if (final_size) *final_size = size;
+    return r;
+}
+
+static const char* check_circuit(const b200_circuit* c) {
+    if (!c) return "b200: null circuit";
+    if (c->po2 < 9 || c->po2 > 22) return "b200: po2 out of range [9,22]";
+    if (c->w_code == 0 || c->w_code % 4 || c->w_data % 4 || c->w_accum % 4 || c->w_accum == 0)
+        return "b200: column widths must be positive multiples of 4";
+    if (c->w_accum > c->w_data) return "b200: w_accum must not exceed w_data";
+    if (c->w_code + c->w_data + c->w_accum > 512) return "b200: too many columns (max 512)";
+    return nullptr;
+}
+
+struct SealLayout {
+    uint32_t off_top[4], off_u, off_fri_top[8], off_final, off_queries, query_words, total;
+    uint32_t q_off_group[4], q_off_fri[8];
+    unsigned rounds; size_t final_size;
+    explicit SealLayout(const b200_circuit& c) {
+        const uint32_t N = 1u << c.po2, D = 4 * N, W = c.w_code + c.w_data + c.w_accum;
+        const uint32_t widths[4] = {c.w_code, c.w_data, c.w_accum, (uint32_t)CHECK_COLS};
+        uint32_t pos = GLOBALS, q = 0;
+        for (int g = 0; g < 4; g++) {
+            MerkleShape m(D, widths[g]);
+            off_top[g] = pos; pos += m.top_size * 8;
+            q_off_group[g] = q; q += m.proof_words();
+        }
+        off_u = pos; pos += (W + c.w_accum + CHECK_COLS) * 4;
+        rounds = fri_rounds(c.po2, &final_size);
+        uint32_t size = N;
+        for (unsigned r = 0; r < rounds; r++) {
+            MerkleShape m(4 * size / FRI_FOLD, 4 * FRI_FOLD);
+            off_fri_top[r] = pos; pos += m.top_size * 8;
+            q_off_fri[r] = q; q += m.proof_words();
+            size /= FRI_FOLD;
+        }
+        off_final = pos; pos += 4 * (uint32_t)final_size;
+        off_queries = pos; query_words = q;
+        total = pos + QUERIES * q;
+    }
+};
+
+static std::atomic<uint64_t> g_launches{0};
+
+// bump allocator over one cudaMalloc'd arena
+struct Arena {
+    uint32_t* base = nullptr; size_t words = 0, used = 0;
+    uint32_t* take(size_t n) { n = (n + 63) & ~(size_t)63; uint32_t* p = base + used; used += n; return p; }
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    Arena arena;
+    // fixed regions (sized for the max circuit)
+    uint32_t *coeffs, *evals, *check_coeffs, *check_evals, *nodes[4];
+    uint32_t *fri_evals, *fri_nodes, *fri_coeffs;
+    uint32_t *combos, *f_planes, *chunk_vals, *chunk_carry, *ev_scratch;
+    uint32_t *pmix, *mp, *chal, *pts, *pos, *seal, *digests;
+    Transcript* tr;
+    GatherTree* d_trees;
+    std::vector<GatherTree> h_trees;
+    uint32_t* h_seal_out = nullptr; size_t seal_words = 0;
+    uint32_t* h_stage = nullptr; size_t h_stage_words = 0;   // pinned staging for child seals
+    bool busy = false;
+};
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_prover {
+    int device = 0;
+    b200_circuit maxc{};
+    const DeviceTables* T = nullptr;
+    std::vector<Slot> slots;
+    size_t device_bytes = 0;
+};
+
+namespace b200 {
+
+static size_t arena_words(const b200_circuit& c) {
+    const size_t N = (size_t)1 << c.po2, D = 4 * N, W = c.w_code + c.w_data + c.w_accum;
+    size_t w = 0;
+    auto add = [&](size_t n) { w += (n + 63) & ~(size_t)63; };
+    add(W * N); add(W * D); add(CHECK_COLS * N); add(CHECK_COLS * D);
+    for (int g = 0; g < 4; g++) add(2 * D * 8);
+    add(16 * N + 16 * N / 8); add(8 * N + 4096); add(4 * N);            // fri evals / nodes / coeffs (geometric sums, padded)
+    add(12 * N); add(4 * N); add(3 * 4 * (N / 2048 + 1)); add(3 * 4 * (N / 2048 + 1));
+    add(evaluate_scratch_words(c.po2, (uint32_t)W));
+    add(4 * (W / 4 + c.w_accum)); add(4 * (W + c.w_accum + CHECK_COLS)); add(64); add(16); add(64);
+    add(SealLayout(c).total); add(64);
+    add(sizeof(Transcript) / 4); add(16 * sizeof(GatherTree) / 4);
+    return w + 1024;
+}
+
+#define CU(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { set_error("b200: %s failed: %s", #x, cudaGetErrorString(e__)); return last_error(); } } while (0)
+
+static const char* slot_init(b200_prover* p, Slot& s) {
+    CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&s.ev_begin)); CU(cudaEventCreate(&s.ev_end));
+    const b200_circuit& c = p->maxc;
+    const size_t N = (size_t)1 << c.po2, D = 4 * N, W = c.w_code + c.w_data + c.w_accum;
+    s.arena.words = arena_words(c);
+    CU(cudaMalloc(&s.arena.base, s.arena.words * 4));
+    p->device_bytes += s.arena.words * 4;
+    Arena& a = s.arena;
+    s.coeffs = a.take(W * N); s.evals = a.take(W * D); s.check_coeffs = a.take(CHECK_COLS * N); s.check_evals = a.take(CHECK_COLS * D);
+    for (int g = 0; g < 4; g++) s.nodes[g] = a.take(2 * D * 8);
+    s.fri_evals = a.take(16 * N + 16 * N / 8); s.fri_nodes = a.take(8 * N + 4096); s.fri_coeffs = a.take(4 * N);
+    s.combos = a.take(12 * N); s.f_planes = a.take(4 * N);
+    s.chunk_vals = a.take(3 * 4 * (N / 2048 + 1)); s.chunk_carry = a.take(3 * 4 * (N / 2048 + 1));
+    s.ev_scratch = a.take(evaluate_scratch_words(c.po2, (uint32_t)W));
+    s.pmix = a.take(4 * (W / 4 + c.w_accum)); s.mp = a.take(4 * (W + c.w_accum + CHECK_COLS));
+    s.chal = a.take(64); s.pts = a.take(16); s.pos = a.take(64);
+    s.seal = a.take(SealLayout(c).total); s.digests = a.take(64);
+    s.tr = reinterpret_cast<Transcript*>(a.take(sizeof(Transcript) / 4));
+    s.d_trees = reinterpret_cast<GatherTree*>(a.take(16 * sizeof(GatherTree) / 4));
+    if (a.used > a.words) { set_error("b200: arena overflow (%zu > %zu words)", a.used, a.words); return last_error(); }
+    return nullptr;
+}
+
+#define KL(x) do { cudaError_t e__ = (x); g_launches.fetch_add(1, std::memory_order_relaxed); if (e__ != cudaSuccess) { set_error("b200: %s: %s", #x, cudaGetErrorString(e__)); return last_error(); } } while (0)
+
+// iNTT + zk_shift (optional) + expand/NTT + leaf hash + tree + top layer to the seal + rng.mix(root)
+static const char* commit_group(b200_prover* p, Slot& s, uint32_t* coeffs, uint32_t* evals, uint32_t* nodes, uint32_t po2,
+                                uint32_t cols, bool interp_shift, uint32_t seal_off) {
+    cudaStream_t st = s.stream;
+    const uint32_t D = 4u << po2;
+    if (interp_shift) {
+        KL(launch_batch_intt(p->T, coeffs, po2, cols, st));             // K1
+        KL(launch_zk_shift(p->T, coeffs, po2, cols, st));               // K2
+    }
+    KL(launch_batch_expand_ntt(p->T, evals, coeffs, po2, INV_RATE_LG, cols, st));   // K3
+    KL(launch_poseidon2_rows(nodes + (size_t)D * 8, evals, D, cols, D, st));         // K4
+    KL(launch_poseidon2_fold_tree(nodes, po2 + 2, st));                               // K5
+    MerkleShape m(D, cols);
+    CU(cudaMemcpyAsync(s.seal + seal_off, nodes + (size_t)m.top_size * 8, (size_t)m.top_size * 32, cudaMemcpyDeviceToDevice, st));
+    KL(launch_iop_commit(s.tr, nodes + 8, st));
+    return nullptr;
+}
+
+// The proof proper.  Precondition: s.seal[8..16) (input digest) is already being produced on s.stream, and for
+// recursion kinds s.digests[0..2) holds the trace seed words.
+static const char* prove_on_slot(b200_prover* p, Slot& s, const b200_circuit& c, uint64_t seed, bool seed_on_device,
+                                 const uint32_t* h_trace, uint32_t* h_seal) {
+    cudaStream_t st = s.stream;
+    const uint32_t po2 = c.po2, N = 1u << po2, D = 4 * N;
+    const uint32_t W = c.w_code + c.w_data + c.w_accum, T = W + c.w_accum + CHECK_COLS;
+    const SealLayout L(c);
+    uint32_t* code = s.coeffs; uint32_t* data = code + (size_t)c.w_code * N; uint32_t* accum = data + (size_t)c.w_data * N;
+    uint32_t* ecode = s.evals; uint32_t* edata = ecode + (size_t)c.w_code * D; uint32_t* eaccum = edata + (size_t)c.w_data * D;
+
+    KL(launch_iop_init(s.tr, st));
+    KL(launch_iop_commit_elems(s.tr, s.seal, GLOBALS, nullptr, st));
+
+    // witness: host trace (H2D) or the witgen stand-in
+    const size_t tw = (size_t)(c.w_code + c.w_data) * N;
+    if (h_trace) CU(cudaMemcpyAsync(code, h_trace, tw * 4, cudaMemcpyHostToDevice, st));
+    else KL(launch_gen_trace(code, seed, seed_on_device ? s.digests : nullptr, tw, st));
+    CU(cudaMemcpyAsync(accum, data, (size_t)c.w_accum * N * 4, cudaMemcpyDeviceToDevice, st));   // raw data columns for accumulate
+
+    const char* e;
+    if ((e = commit_group(p, s, code, ecode, s.nodes[0], po2, c.w_code, true, L.off_top[0]))) return e;
+    if ((e = commit_group(p, s, data, edata, s.nodes[1], po2, c.w_data, true, L.off_top[1]))) return e;
+
+    uint32_t* accum_mix = s.chal; uint32_t* poly_mix = s.chal + 4; uint32_t* z = s.chal + 8; uint32_t* mix = s.chal + 12;
+    uint32_t* fri_mix = s.chal + 16;
+    KL(launch_iop_draw_ext(s.tr, accum_mix, 1, st));
+    KL(launch_accumulate(accum, N, c.w_accum, accum_mix, st));
+    if ((e = commit_group(p, s, accum, eaccum, s.nodes[2], po2, c.w_accum, true, L.off_top[2]))) return e;
+
+    // constraint stand-in over the 4N domain -> 4 planes x 4N -> iNTT -> 16 columns x N
+    KL(launch_iop_draw_ext(s.tr, poly_mix, 1, st));
+    KL(launch_powers(s.pmix, poly_mix, W / 4 + c.w_accum, st));
+    KL(launch_eval_check(s.check_coeffs, s.evals, po2 + 2, c.w_code, c.w_data, c.w_accum, s.pmix, st));
+    KL(launch_batch_intt(p->T, s.check_coeffs, po2 + 2, 4, st));
+    if ((e = commit_group(p, s, s.check_coeffs, s.check_evals, s.nodes[3], po2, CHECK_COLS, false, L.off_top[3]))) return e;
+
+    // DEEP point and tap evaluations (K7), written straight into the seal
+    KL(launch_iop_draw_ext(s.tr, z, 1, st));
+    KL(launch_deep_points(s.pts, z, p->T->rou_rev[po2], st));
+    uint32_t* u = s.seal + L.off_u;
+    KL(launch_evaluate(u, u + 4 * (size_t)W, s.coeffs, po2, W, s.pts, s.pts + 4, W - c.w_accum, W, s.ev_scratch, st));
+    KL(launch_evaluate(u + 4 * (size_t)(W + c.w_accum), nullptr, s.check_coeffs, po2, CHECK_COLS, s.pts + 8, nullptr, 0, 0, s.ev_scratch, st));
+    KL(launch_iop_commit_elems(s.tr, u, T * 4, nullptr, st));
+
+    // DEEP combination (K8)
+    KL(launch_iop_draw_ext(s.tr, mix, 1, st));
+    KL(launch_powers(s.mp, mix, T, st));
+    DeepArgs da{s.coeffs, s.check_coeffs, u, s.mp, s.pts, s.combos, s.chunk_vals, s.chunk_carry, s.f_planes, po2, W, c.w_accum};
+    KL(launch_deep(da, st));
+
+    // FRI commit phase
+    s.h_trees.clear();
+    const uint32_t widths[4] = {c.w_code, c.w_data, c.w_accum, (uint32_t)CHECK_COLS};
+    const uint32_t* gev[4] = {ecode, edata, eaccum, s.check_evals};
+    for (int g = 0; g < 4; g++) {
+        MerkleShape m(D, widths[g]);
+        s.h_trees.push_back(GatherTree{gev[g], s.nodes[g], D, widths[g], m.top_size, L.q_off_group[g], 0});
+    }
+    uint32_t* cur = s.f_planes; uint32_t size = N, lg = po2;
+    uint32_t* fev = s.fri_evals; uint32_t* fnodes = s.fri_nodes; uint32_t* fco = s.fri_coeffs;
+    for (unsigned r = 0; r < L.rounds; r++) {
+        const uint32_t dom = 4 * size, rows = dom / FRI_FOLD;
+        KL(launch_batch_expand_ntt(p->T, fev, cur, lg, INV_RATE_LG, 4, st));
+        KL(launch_poseidon2_rows(fnodes + (size_t)rows * 8, fev, rows, 4 * FRI_FOLD, rows, st));
+        KL(launch_poseidon2_fold_tree(fnodes, ilog2(rows), st));
+        MerkleShape m(rows, 4 * FRI_FOLD);
+        CU(cudaMemcpyAsync(s.seal + L.off_fri_top[r], fnodes + (size_t)m.top_size * 8, (size_t)m.top_size * 32, cudaMemcpyDeviceToDevice, st));
+        KL(launch_iop_commit(s.tr, fnodes + 8, st));
+        KL(launch_iop_draw_ext(s.tr, fri_mix, 1, st));
+        KL(launch_fri_fold(fco, cur, size, fri_mix, st));
+        s.h_trees.push_back(GatherTree{fev, fnodes, rows, 4 * FRI_FOLD, m.top_size, L.q_off_fri[r], rows});
+        cur = fco; fco += 4 * (size_t)(size / FRI_FOLD);
+        fev += 4 * (size_t)dom; fnodes += 2 * (size_t)rows * 8;
+        size /= FRI_FOLD; lg -= 4;
+    }
+    CU(cudaMemcpyAsync(s.seal + L.off_final, cur, (size_t)4 * size * 4, cudaMemcpyDeviceToDevice, st));
+    KL(launch_iop_commit_elems(s.tr, s.seal + L.off_final, 4 * size, nullptr, st));
+
+    // query phase (K9)
+    KL(launch_iop_draw_bits(s.tr, s.pos, QUERIES, po2 + 2, st));
+    CU(cudaMemcpyAsync(s.d_trees, s.h_trees.data(), s.h_trees.size() * sizeof(GatherTree), cudaMemcpyHostToDevice, st));
+    KL(launch_gather_queries(s.seal, L.off_queries, L.query_words, s.pos, s.d_trees, (uint32_t)s.h_trees.size(), st));
+
+    CU(cudaMemcpyAsync(h_seal, s.seal, (size_t)L.total * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(s.ev_end, st));
+    s.busy = true; s.h_seal_out = h_seal; s.seal_words = L.total;
+    return nullptr;
+}
+
+// digest of a seal held in host memory -> d_out8 (device): 1024-row column-major view, hash_rows, fold (K4/K5)
+static const char* seal_digest_async(b200_prover* p, Slot& s, const uint32_t* h_seal, size_t words, uint32_t* h_stage,
+                                     uint32_t* d_scratch_matrix, uint32_t* d_scratch_nodes, uint32_t* d_out8) {
+    (void)p;
+    const uint32_t rows = 1024; const size_t cols = (words + rows - 1) / rows;
+    memcpy(h_stage, h_seal, words * 4);
+    CU(cudaMemsetAsync(d_scratch_matrix, 0, cols * rows * 4, s.stream));
+    CU(cudaMemcpyAsync(d_scratch_matrix, h_stage, words * 4, cudaMemcpyHostToDevice, s.stream));
+    KL(launch_poseidon2_rows(d_scratch_nodes + (size_t)rows * 8, d_scratch_matrix, rows, (uint32_t)cols, rows, s.stream));
+    KL(launch_poseidon2_fold_tree(d_scratch_nodes, 10, s.stream));
+    CU(cudaMemcpyAsync(d_out8, d_scratch_nodes + 8, 32, cudaMemcpyDeviceToDevice, s.stream));
+    return nullptr;
+}
+
+}  // namespace b200
+
+extern "C" {
+
+uint64_t b200_kernel_launches(void) { return g_launches.load(); }
+
+size_t b200_seal_words(const b200_circuit* c) {
+    if (check_circuit(c)) return 0;
+    return SealLayout(*c).total;
+}
+
+const char* b200_prover_create(b200_prover** out, int device, const b200_circuit* maxc, uint32_t slots) {
+    if (!out) return "b200: null out";
+    *out = nullptr;
+    const char* ce = check_circuit(maxc);
+    if (ce) { set_error("%s", ce); return last_error(); }
+    if (slots == 0 || slots > 16) { set_error("b200: slots must be in [1,16]"); return last_error(); }
+    const DeviceTables* T = get_tables(device);
+    if (!T) return last_error();
+    CU(cudaSetDevice(device));
+    b200_prover* p = new (std::nothrow) b200_prover();
+    if (!p) { set_error("b200: out of host memory"); return last_error(); }
+    p->device = device; p->maxc = *maxc; p->T = T;
+    p->slots.resize(slots);
+    for (auto& s : p->slots) {
+        const char* e = slot_init(p, s);
+        if (e) { b200_prover_destroy(p); return e; }
+        const size_t stage_words = 2 * (SealLayout(*maxc).total + 4096);
+        if (cudaHostAlloc((void**)&s.h_stage, stage_words * 4, cudaHostAllocDefault) != cudaSuccess) {
+            set_error("b200: cudaHostAlloc failed"); b200_prover_destroy(p); return last_error();
+        }
+        s.h_stage_words = stage_words;
+    }
+    *out = p;
+    return nullptr;
+}
+
+void b200_prover_destroy(b200_prover* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    for (auto& s : p->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        if (s.arena.base) cudaFree(s.arena.base);
+        if (s.h_stage) cudaFreeHost(s.h_stage);
+        if (s.ev_begin) cudaEventDestroy(s.ev_begin);
+        if (s.ev_end) cudaEventDestroy(s.ev_end);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    delete p;
+}
+
+size_t b200_prover_device_bytes(const b200_prover* p) { return p ? p->device_bytes : 0; }
+
+static const char* slot_check(b200_prover* p, uint32_t slot, const b200_circuit* c) {
+    if (!p) { set_error("b200: null prover"); return last_error(); }
+    if (slot >= p->slots.size()) { set_error("b200: slot %u out of range", slot); return last_error(); }
+    const char* ce = check_circuit(c);
+    if (ce) { set_error("%s", ce); return last_error(); }
+    if (c->po2 > p->maxc.po2 || c->w_code + c->w_data + c->w_accum > p->maxc.w_code + p->maxc.w_data + p->maxc.w_accum ||
+        c->w_accum > p->maxc.w_accum) { set_error("b200: circuit exceeds the prover's max_circuit"); return last_error(); }
+    if (p->slots[slot].busy) { set_error("b200: slot %u busy (call b200_prover_wait first)", slot); return last_error(); }
+    CU(cudaSetDevice(p->device));
+    return nullptr;
+}
+
+const char* b200_prove_segment_async(b200_prover* p, uint32_t slot, const b200_circuit* c, uint64_t seed, const uint32_t* h_trace,
+                                     uint32_t* h_seal) {
+    const char* e = slot_check(p, slot, c);
+    if (e) return e;
+    if (!h_seal) { set_error("b200: null h_seal"); return last_error(); }
+    Slot& s = p->slots[slot];
+    CU(cudaEventRecord(s.ev_begin, s.stream));
+    KL(launch_set_globals(s.seal, c->po2, c->w_code, c->w_data, c->w_accum, c->kind, seed, 1, s.stream));
+    return prove_on_slot(p, s, *c, seed, false, h_trace, h_seal);
+}
+
+const char* b200_recursion_async(b200_prover* p, uint32_t slot, const b200_circuit* c, const uint32_t* h_a, size_t wa,
+                                 const uint32_t* h_b, size_t wb, uint32_t* h_seal) {
+    const char* e = slot_check(p, slot, c);
+    if (e) return e;
+    if (!h_seal || !h_a || wa == 0) { set_error("b200: null argument"); return last_error(); }
+    Slot& s = p->slots[slot];
+    if (wa + wb > s.h_stage_words) { set_error("b200: child seal too large"); return last_error(); }
+    CU(cudaEventRecord(s.ev_begin, s.stream));
+    KL(launch_set_globals(s.seal, c->po2, c->w_code, c->w_data, c->w_accum, c->kind, 0, 0, s.stream));
+    // scratch: the evaluation / node regions are free until the proof starts
+    if ((e = seal_digest_async(p, s, h_a, wa, s.h_stage, s.evals, s.nodes[0], s.digests + 8))) return e;
+    if (h_b && wb) {
+        if ((e = seal_digest_async(p, s, h_b, wb, s.h_stage + wa, s.evals, s.nodes[0], s.digests + 16))) return e;
+        KL(launch_hash_pair_one(s.seal + 8, s.digests + 8, s.digests + 16, s.stream));
+    } else {
+        CU(cudaMemcpyAsync(s.seal + 8, s.digests + 8, 32, cudaMemcpyDeviceToDevice, s.stream));
+    }
+    // trace seed = first two words of the input digest
+    CU(cudaMemcpyAsync(s.digests, s.seal + 8, 8, cudaMemcpyDeviceToDevice, s.stream));
+    return prove_on_slot(p, s, *c, 0, true, nullptr, h_seal);
+}
+
+const char* b200_prover_wait(b200_prover* p, uint32_t slot) {
+    if (!p || slot >= p->slots.size()) { set_error("b200: bad prover/slot"); return last_error(); }
+    Slot& s = p->slots[slot];
+    CU(cudaSetDevice(p->device));
+    CU(cudaStreamSynchronize(s.stream));
+    s.busy = false;
+    return nullptr;
+}
+
+float b200_prover_last_ms(b200_prover* p, uint32_t slot) {
+    if (!p || slot >= p->slots.size()) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, p->slots[slot].ev_begin, p->slots[slot].ev_end) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+const char* b200_host_alloc(void** out, size_t bytes) {
+    if (!out) return "b200: null out";
+    CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return nullptr;
+}
+void b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// Per-device read-only tables (stage twiddles, six-step twiddle decomposition, zk_shift powers) and the
+// host-side BabyBear helpers used to build them.  Product code: independent of oracle/.
+#include "internal.h"
+#include "constants.inc"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace b200 {
+
+static constexpr uint32_t HP = 2013265921u, HPINV = 0x88000001u, HR2 = 1172168163u;
+
+uint32_t h_mul(uint32_t a, uint32_t b) {
+    uint64_t o = (uint64_t)a * b;
+    uint32_t m = (uint32_t)o * HPINV;
+    uint32_t t = (uint32_t)(((uint64_t)m * HP) >> 32);
+    uint32_t hi = (uint32_t)(o >> 32);
+    return hi >= t ? hi - t : hi - t + HP;
+}
+uint32_t h_add(uint32_t a, uint32_t b) { uint32_t s = a + b; return s >= HP ? s - HP : s; }
+uint32_t h_sub(uint32_t a, uint32_t b) { return a >= b ? a - b : a - b + HP; }
+uint32_t h_to_mont(uint32_t x) { return h_mul(x % HP, HR2); }
+uint32_t h_from_mont(uint32_t a) { return h_mul(a, 1u); }
+uint32_t h_pow(uint32_t a, uint64_t e) {
+    uint32_t r = h_to_mont(1);
+    while (e) { if (e & 1) r = h_mul(r, a); a = h_mul(a, a); e >>= 1; }
+    return r;
+}
+uint32_t h_inv(uint32_t a) { return h_pow(a, HP - 2); }
+
+static thread_local char g_err[1024];
+const char* last_error() { return g_err; }
+void set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+}
+
+static std::mutex g_mu;
+static DeviceTables* g_tables[64];
+
+static uint32_t* upload(const std::vector<uint32_t>& v) {
+    uint32_t* d = nullptr;
+    if (cudaMalloc(&d, v.size() * 4) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+    return d;
+}
+
+const DeviceTables* get_tables(int device) {
+    if (device < 0 || device >= 64) { set_error("b200: bad device %d", device); return nullptr; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_tables[device]) return g_tables[device];
+    int prev = 0; cudaGetDevice(&prev);
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("b200: cudaSetDevice(%d) failed", device); return nullptr; }
+    DeviceTables* T = new DeviceTables();
+    memset(T, 0, sizeof *T);
+    T->device = device;
+    memcpy(T->rou_fwd, B200_ROU_FWD_MONT, sizeof T->rou_fwd);
+    memcpy(T->rou_rev, B200_ROU_REV_MONT, sizeof T->rou_rev);
+    bool ok = true;
+    // stage twiddles: tw[2^(l-1) + i] = w_{2^l}^i for l <= 13
+    const int TWL = 13;
+    for (int inv = 0; inv < 2; inv++) {
+        std::vector<uint32_t> tw((size_t)1 << TWL, h_to_mont(1));
+        for (int l = 1; l <= TWL; l++) {
+            uint32_t w = inv ? T->rou_rev[l] : T->rou_fwd[l], cur = h_to_mont(1);
+            for (uint32_t i = 0; i < (1u << (l - 1)); i++) { tw[(1u << (l - 1)) + i] = cur; cur = h_mul(cur, w); }
+        }
+        uint32_t* d = upload(tw);
+        ok &= d != nullptr;
+        (inv ? T->tw_inv : T->tw_fwd) = d;
+    }
+    // six-step decomposition tables
+    for (int m = 1; m <= MAX_LG && ok; m++) {
+        const int h = (m + 1) / 2;
+        for (int inv = 0; inv < 2; inv++) {
+            const uint32_t w = inv ? T->rou_rev[m] : T->rou_fwd[m];
+            std::vector<uint32_t> t(((size_t)1 << h) + ((size_t)1 << (m - h)));
+            uint32_t cur = h_to_mont(1);
+            for (uint32_t i = 0; i < (1u << h); i++) { t[i] = cur; cur = h_mul(cur, w); }
+            const uint32_t wh = h_pow(w, (uint64_t)1 << h);
+            cur = inv ? h_inv(h_to_mont(1u << m)) : h_to_mont(1);      // fold 1/2^m into the inverse hi table
+            for (uint32_t i = 0; i < (1u << (m - h)); i++) { t[((size_t)1 << h) + i] = cur; cur = h_mul(cur, wh); }
+            uint32_t* d = upload(t);
+            ok &= d != nullptr;
+            (inv ? T->pow_inv : T->pow_fwd)[m] = d;
+        }
+    }
+    // zk_shift tables
+    {
+        std::vector<uint32_t> lo(4096), hi(4096);
+        const uint32_t three = h_to_mont(3), step = h_pow(three, 4096);
+        uint32_t cur = h_to_mont(1);
+        for (int i = 0; i < 4096; i++) { lo[i] = cur; cur = h_mul(cur, three); }
+        cur = h_to_mont(1);
+        for (int i = 0; i < 4096; i++) { hi[i] = cur; cur = h_mul(cur, step); }
+        T->p3lo = upload(lo); T->p3hi = upload(hi);
+        ok &= T->p3lo && T->p3hi;
+    }
+    cudaSetDevice(prev);
+    if (!ok) { set_error("b200: table upload failed: %s", cudaGetErrorString(cudaGetLastError())); delete T; return nullptr; }
+    g_tables[device] = T;
+    return T;
+}
+
+}  // namespace b200

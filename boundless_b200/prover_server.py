@@ -1,0 +1,198 @@
+"""Host-side mirror of the reference's operator boundary for the segment-proving path.
+
+The bento GPU agent holds `Rc<dyn risc0_zkvm::ProverServer>` obtained from
+`get_prover_server(&ProverOpts::default())` (/root/reference/prover/crates/workflow/src/lib.rs:276-284) and calls
+`prove_segment` (tasks/prove.rs:44-52), `lift` (:96-104), `join` (tasks/join.rs:52-56), `resolve`
+(tasks/resolve.rs:84-88) and `union` (tasks/union.rs:43-47) on it.  This module keeps those names and argument
+meanings over the C ABI of libb200zkp.so; errors surface as exceptions the way the reference surfaces
+`anyhow::Error` (the agent turns any Err into a task retry, workflow/src/lib.rs:639-677).
+
+Synthetic circuit: the rv32im witgen / eval_check are out of scope, so a `Segment` is
+(index, po2, seed[, host trace]) and receipts carry the seal words plus the claim metadata needed by lift/join.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import lib as _lib
+from .lib import B200Error, Circuit
+
+KIND_SEGMENT, KIND_LIFT, KIND_JOIN, KIND_RESOLVE, KIND_UNION = range(5)
+SEGMENT_WIDTHS = (16, 208, 32)       # code / data / accum
+RECURSION_WIDTHS = (16, 128, 16)     # placeholder widths of the recursion circuit (po2 = 18)
+RECURSION_PO2 = 18
+SEED_BASE = 0xB2000000               # segment i uses seed SEED_BASE + i
+
+
+@dataclass
+class ProverOpts:
+    """Stand-in for risc0_zkvm::ProverOpts: the shapes the prover is provisioned for."""
+    segment_po2: int = 20                      # agent default --segment-po2 (workflow/src/lib.rs:83-84)
+    segment_widths: tuple = SEGMENT_WIDTHS
+    recursion_po2: int = RECURSION_PO2
+    recursion_widths: tuple = RECURSION_WIDTHS
+    slots: int = 2                             # proofs in flight per GPU
+    device: int = 0
+
+
+@dataclass
+class Segment:
+    """What the executor emits per 2^po2 cycles (tasks/executor.rs:721-757), synthetic form."""
+    index: int
+    po2: int = 20
+    seed: Optional[int] = None
+    trace: Optional[np.ndarray] = None         # optional host witness (w_code + w_data) x 2^po2, Montgomery u32
+
+    def __post_init__(self):
+        if self.seed is None:
+            self.seed = SEED_BASE + self.index
+
+
+@dataclass
+class SegmentReceipt:
+    seal: np.ndarray
+    index: int
+    po2: int
+
+    def get_seal_bytes(self):
+        return self.seal.tobytes()
+
+
+@dataclass
+class SuccinctReceipt:
+    seal: np.ndarray
+    kind: int
+    claim: tuple = field(default_factory=tuple)   # (first_segment, last_segment) covered by this receipt
+
+
+class VerifierContext:
+    """Placeholder for risc0_zkvm::VerifierContext (prove.rs:44): carries nothing on the synthetic path."""
+
+
+class _Pinned:
+    def __init__(self, L, words):
+        self.L = L
+        p = C.c_void_p()
+        _lib.check(L.b200_host_alloc(C.byref(p), max(words, 1) * 4))
+        self.ptr = p
+        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(max(words, 1),))
+
+    def free(self):
+        if self.ptr:
+            self.L.b200_host_free(self.ptr)
+            self.ptr = None
+
+
+class ProverServer:
+    """One per GPU process, like the agent's `Rc<dyn ProverServer>` (not thread-safe, one task loop)."""
+
+    def __init__(self, opts: ProverOpts):
+        self.opts = opts
+        self.L = _lib.require_gpu(opts.device)
+        sw, rw = opts.segment_widths, opts.recursion_widths
+        self.seg_circuit = Circuit(opts.segment_po2, sw[0], sw[1], sw[2], KIND_SEGMENT)
+        # arena is sized for the larger of the two shapes
+        maxc = Circuit(max(opts.segment_po2, opts.recursion_po2), max(sw[0], rw[0]), max(sw[1], rw[1]), max(sw[2], rw[2]), 0)
+        h = C.c_void_p()
+        _lib.check(self.L.b200_prover_create(C.byref(h), opts.device, C.byref(maxc), opts.slots))
+        self.h = h
+        max_words = max(self.seal_words(self.seg_circuit), self.seal_words(self._rec_circuit(KIND_LIFT)))
+        self._seal_bufs = [_Pinned(self.L, max_words) for _ in range(opts.slots)]
+        self._pending = [None] * opts.slots
+
+    # -- helpers -------------------------------------------------------------------------------------------
+    def _rec_circuit(self, kind):
+        rw = self.opts.recursion_widths
+        return Circuit(self.opts.recursion_po2, rw[0], rw[1], rw[2], kind)
+
+    def seal_words(self, circuit):
+        return self.L.b200_seal_words(C.byref(circuit))
+
+    def device_bytes(self):
+        return self.L.b200_prover_device_bytes(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            for s in range(self.opts.slots):
+                if self._pending[s] is not None:
+                    self.L.b200_prover_wait(self.h, s)
+            self.L.b200_prover_destroy(self.h)
+            self.h = None
+            for b in self._seal_bufs:
+                b.free()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- asynchronous form (one proof in flight per slot) -------------------------------------------------
+    def submit_segment(self, slot, segment: Segment):
+        c = Circuit(segment.po2, *self.opts.segment_widths, KIND_SEGMENT)
+        tr = None
+        if segment.trace is not None:
+            tr = np.ascontiguousarray(segment.trace, dtype=np.uint32)
+            need = (c.w_code + c.w_data) << c.po2
+            if tr.size != need:
+                raise B200Error("segment trace has %d words, expected %d" % (tr.size, need))
+        _lib.check(self.L.b200_prove_segment_async(self.h, slot, C.byref(c), segment.seed,
+                                                    tr.ctypes.data_as(C.c_void_p) if tr is not None else None,
+                                                    self._seal_bufs[slot].ptr))
+        self._pending[slot] = ("segment", c, segment, tr)
+
+    def submit_recursion(self, slot, kind, a, b=None):
+        c = self._rec_circuit(kind)
+        sa = np.ascontiguousarray(a.seal, dtype=np.uint32)
+        sb = np.ascontiguousarray(b.seal, dtype=np.uint32) if b is not None else None
+        _lib.check(self.L.b200_recursion_async(self.h, slot, C.byref(c), sa.ctypes.data_as(C.c_void_p), sa.size,
+                                               sb.ctypes.data_as(C.c_void_p) if sb is not None else None,
+                                               sb.size if sb is not None else 0, self._seal_bufs[slot].ptr))
+        self._pending[slot] = ("recursion", c, (kind, a, b), (sa, sb))
+
+    def wait(self, slot):
+        pend = self._pending[slot]
+        if pend is None:
+            raise B200Error("slot %d has no proof in flight" % slot)
+        _lib.check(self.L.b200_prover_wait(self.h, slot))
+        self._pending[slot] = None
+        what, c, arg, _keep = pend
+        seal = self._seal_bufs[slot].array[: self.seal_words(c)].copy()
+        if what == "segment":
+            return SegmentReceipt(seal, arg.index, arg.po2)
+        kind, a, b = arg
+        lo = a.claim[0] if isinstance(a, SuccinctReceipt) else a.index
+        last = b if b is not None else a
+        hi = last.claim[1] if isinstance(last, SuccinctReceipt) else last.index
+        return SuccinctReceipt(seal, kind, (lo, hi))
+
+    def last_ms(self, slot):
+        return float(self.L.b200_prover_last_ms(self.h, slot))
+
+    # -- the reference's method names (synchronous, slot 0) -------------------------------------------------
+    def prove_segment(self, ctx: VerifierContext, segment: Segment) -> SegmentReceipt:
+        self.submit_segment(0, segment)
+        return self.wait(0)
+
+    def lift(self, receipt: SegmentReceipt) -> SuccinctReceipt:
+        self.submit_recursion(0, KIND_LIFT, receipt)
+        return self.wait(0)
+
+    def join(self, a: SuccinctReceipt, b: SuccinctReceipt) -> SuccinctReceipt:
+        self.submit_recursion(0, KIND_JOIN, a, b)
+        return self.wait(0)
+
+    def resolve(self, conditional: SuccinctReceipt, assumption: SuccinctReceipt) -> SuccinctReceipt:
+        self.submit_recursion(0, KIND_RESOLVE, conditional, assumption)
+        return self.wait(0)
+
+    def union(self, a: SuccinctReceipt, b: SuccinctReceipt) -> SuccinctReceipt:
+        self.submit_recursion(0, KIND_UNION, a, b)
+        return self.wait(0)
+
+
+def get_prover_server(opts: Optional[ProverOpts] = None) -> ProverServer:
+    """Mirror of risc0_zkvm::get_prover_server(&ProverOpts) (workflow/src/lib.rs:276-284)."""
+    return ProverServer(opts or ProverOpts())

@@ -1,0 +1,125 @@
+/*
+ * b200zkp.h -- C ABI of libb200zkp.so: B200-native (sm_100a) kernels and prover pipeline for the
+ * segment-proving hot path of boundless-xyz/boundless (bento GPU agent -> risc0_zkvm::ProverServer).
+ *
+ * Every entry point returns `const char*`: NULL on success, otherwise a thread-local message (the same
+ * convention as risc0-sys' C wrappers; SURVEY.md 8b "Errors").  Device buffers are caller-owned raw device
+ * pointers; elements are u32 BabyBear values in Montgomery form; matrices are column-major (column c occupies
+ * [c*rows, (c+1)*rows)); a digest is 8 Montgomery words.  `stream` is a cudaStream_t passed as void*.
+ * No entry point falls back to the CPU: without a usable CUDA device every call fails with a message.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference):
+ *   - trait risc0_zkvm::ProverServer obtained at prover/crates/workflow/src/lib.rs:276-284 and called at
+ *     prover/crates/workflow/src/tasks/prove.rs:44-52 (prove_segment), :96-104 (lift),
+ *     tasks/join.rs:52-56 (join), tasks/resolve.rs:84-88 (resolve), tasks/union.rs:43-47 (union);
+ *   - one layer down, the extern "C" surface of risc0-sys 1.5.0 / sppark 0.1.14 (Cargo.lock:9131,10315;
+ *     un-vendored): sppark_batch_iNTT / sppark_batch_NTT / sppark_batch_expand / sppark_batch_zk_shift /
+ *     sppark_poseidon2_rows / sppark_poseidon2_fold / fri_fold / batch_evaluate_any.
+ */
+#ifndef B200ZKP_H
+#define B200ZKP_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_DIGEST_WORDS 8
+#define B200_QUERIES 50
+#define B200_CHECK_COLS 16
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+/* replaces sppark_init(): selects the device and builds the twiddle tables (idempotent). */
+const char* b200_init(int device);
+const char* b200_last_error(void);
+/* number of CUDA devices visible, or -1 (never touches the CPU path) */
+int b200_device_count(void);
+
+/* ---- kernel 1: NTT (replaces sppark_batch_iNTT / _NTT / _expand / _zk_shift) ------------------------------ */
+/* K1: `count` in-place iNTTs of size 2^lg_n: natural-order evaluations -> bit-reversed coefficients, x 2^-lg_n */
+const char* b200_batch_intt(uint32_t* d_io, uint32_t lg_n, uint32_t count, void* stream);
+/* forward: bit-reversed coefficients -> natural-order evaluations, in place */
+const char* b200_batch_ntt(uint32_t* d_io, uint32_t lg_n, uint32_t count, void* stream);
+/* K3: d_out[count][2^(lg_n+lg_blowup)] = evaluations of the zero-padded polynomials (expand + NTT, levels skipped) */
+const char* b200_batch_expand_ntt(uint32_t* d_out, const uint32_t* d_in, uint32_t lg_n, uint32_t lg_blowup,
+                                  uint32_t count, void* stream);
+/* K2: coefficient of x^d *= 3^d (slot j holds degree bitrev(j)) */
+const char* b200_batch_zk_shift(uint32_t* d_io, uint32_t lg_n, uint32_t count, void* stream);
+const char* b200_batch_bit_reverse(uint32_t* d_io, uint32_t lg_n, uint32_t count, void* stream);
+
+/* ---- kernel 2: Poseidon2 (replaces sppark_poseidon2_rows / sppark_poseidon2_fold) ---------------------------- */
+/* K4: d_out[rows][8]; leaf j = sponge over d_matrix[c*rows + j], c < cols */
+const char* b200_poseidon2_rows(uint32_t* d_out, const uint32_t* d_matrix, uint32_t rows, uint32_t cols, void* stream);
+/* K5 (one layer): d_out[i] = hash_pair(d_in[2i], d_in[2i+1]), i < num_hashes */
+const char* b200_poseidon2_fold(uint32_t* d_out, const uint32_t* d_in, uint32_t num_hashes, void* stream);
+/* K4+K5: whole tree. d_nodes holds 2*rows digests: leaves at [rows,2rows), node i = hash_pair(2i, 2i+1), root = node 1 */
+const char* b200_merkle_tree(uint32_t* d_nodes, const uint32_t* d_matrix, uint32_t lg_rows, uint32_t cols, void* stream);
+
+/* ---- kernel 3: FRI fold + evaluation (replaces fri_fold, batch_evaluate_any) ------------------------------------ */
+/* K6: d_in = 4 planes x in_size bit-reversed coefficients, d_out = 4 planes x in_size/16, d_mix = one Fp4 (device) */
+const char* b200_fri_fold(uint32_t* d_out, const uint32_t* d_in, uint32_t in_size, const uint32_t* d_mix, void* stream);
+/* K7: d_out[count][4] = value of each bit-reversed coefficient column at the Fp4 point d_x (device) */
+size_t b200_evaluate_scratch_words(uint32_t lg_n, uint32_t count);
+const char* b200_batch_evaluate_any(uint32_t* d_out, const uint32_t* d_coeffs, uint32_t lg_n, uint32_t count,
+                                    const uint32_t* d_x, uint32_t* d_scratch, void* stream);
+
+/* ---- prover pipeline (the ProverServer operator boundary) ------------------------------------------------------- */
+typedef struct {
+    uint32_t po2;                       /* trace rows = 2^po2; reference default 20 (workflow/src/lib.rs:83-84) */
+    uint32_t w_code, w_data, w_accum;   /* synthetic column-group widths; segment default 16/208/32 */
+    uint32_t kind;                      /* 0 segment, 1 lift, 2 join, 3 resolve, 4 union */
+} b200_circuit;
+
+typedef struct b200_prover b200_prover;
+
+size_t b200_seal_words(const b200_circuit* c);
+/* one prover per GPU process (the agent's `Rc<dyn ProverServer>`); `slots` proofs may be in flight at once */
+const char* b200_prover_create(b200_prover** out, int device, const b200_circuit* max_circuit, uint32_t slots);
+void b200_prover_destroy(b200_prover* p);
+size_t b200_prover_device_bytes(const b200_prover* p);
+
+/* prove_segment: enqueue the whole proof on the slot's stream and return immediately.
+ * h_trace (optional, may be NULL) = (w_code + w_data) x 2^po2 Montgomery words in host memory (pinned for overlap):
+ * the segment's witness; when NULL the witgen stand-in expands `seed` on the device.
+ * h_seal receives b200_seal_words(c) words once b200_prover_wait(p, slot) returns. */
+const char* b200_prove_segment_async(b200_prover* p, uint32_t slot, const b200_circuit* c, uint64_t seed,
+                                     const uint32_t* h_trace, uint32_t* h_seal);
+/* lift / join / resolve / union: recursion-shaped proof (kind 1..4) over the digest(s) of the child seal(s) */
+const char* b200_recursion_async(b200_prover* p, uint32_t slot, const b200_circuit* c, const uint32_t* h_seal_a,
+                                 size_t words_a, const uint32_t* h_seal_b, size_t words_b, uint32_t* h_seal);
+const char* b200_prover_wait(b200_prover* p, uint32_t slot);
+/* device time (ms) between the first and last operation of the slot's last proof */
+float b200_prover_last_ms(b200_prover* p, uint32_t slot);
+/* number of kernels this library launched since load (all threads) */
+uint64_t b200_kernel_launches(void);
+/* host-pinned allocation helpers for h_trace / h_seal */
+const char* b200_host_alloc(void** out, size_t bytes);
+void b200_host_free(void* p);
+
+/* ---- join-tree planner (mirrors taskdb::planner::Planner, prover/crates/taskdb/src/planner/mod.rs:91-240) -------- */
+typedef struct b200_planner b200_planner;
+enum { B200_CMD_KECCAK = 0, B200_CMD_FINALIZE = 1, B200_CMD_JOIN = 2, B200_CMD_SEGMENT = 3, B200_CMD_UNION = 4 };
+/* mirrors planner::task::Task (prover/crates/taskdb/src/planner/task.rs:17-24) */
+typedef struct {
+    uint32_t task_number, task_height, command;
+    uint32_t n_depends_on, depends_on[2];
+    uint32_t n_keccak_depends_on, keccak_depends_on[2];
+} b200_task;
+b200_planner* b200_planner_new(void);
+void b200_planner_free(b200_planner* pl);
+/* return the new task number, or -1 "PlanFinalized" */
+int64_t b200_planner_enqueue_segment(b200_planner* pl);
+int64_t b200_planner_enqueue_keccak(b200_planner* pl);
+/* joins the remaining peaks right-to-left, appends Finalize; returns its task number, or -1 "PlanNotStarted" */
+int64_t b200_planner_finish(b200_planner* pl);
+size_t b200_planner_task_count(const b200_planner* pl);
+/* 0 on success, -1 "Invalid task number" */
+int b200_planner_get_task(const b200_planner* pl, size_t task_number, b200_task* out);
+/* iterator over tasks in creation order (Planner::next_task); 0 = produced a task, 1 = none pending */
+int b200_planner_next_task(b200_planner* pl, b200_task* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,213 @@
+"""Bit-exact parity of every C-ABI kernel entry point against the CPU oracle (SURVEY.md 7 acceptance (iii)).
+
+All calls go through libb200zkp.so's extern "C" surface with raw device pointers (torch only owns the memory).
+Integer work: the bar is bit-exact equality.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+P = 2013265921
+
+
+def dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def ck(err):
+    assert err is None, err
+
+
+def rand_elems(rng, n, oracle):
+    return oracle.to_mont(rng.integers(0, P, n, dtype=np.int64))
+
+
+EDGE = ["zero", "pm1", "equal"]
+
+
+def edge_input(kind, n, oracle):
+    if kind == "zero":
+        return np.zeros(n, np.uint32)
+    if kind == "pm1":
+        return oracle.to_mont(np.full(n, P - 1, np.int64))
+    return oracle.to_mont(np.full(n, 123456789, np.int64))
+
+
+@pytest.mark.parametrize("lg_n,count", [(1, 3), (4, 5), (10, 1), (10, 16), (11, 3), (12, 7), (13, 3), (14, 16), (15, 2),
+                                        (16, 16), (18, 3), (20, 2)])
+def test_batch_intt_and_shift(gpu, b200lib, oracle, lg_n, count):
+    torch = gpu
+    rng = np.random.default_rng(lg_n * 100 + count)
+    a = rand_elems(rng, count << lg_n, oracle)
+    d = dev(torch, a)
+    ck(b200lib.b200_batch_intt(ptr(d), lg_n, count, None))
+    torch.cuda.synchronize()
+    ref = oracle.batch_intt(a, lg_n, count)
+    assert np.array_equal(host(d), ref)
+    ck(b200lib.b200_batch_zk_shift(ptr(d), lg_n, count, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(host(d), oracle.batch_zk_shift(ref, lg_n, count))
+
+
+@pytest.mark.parametrize("lg_n,count", [(1, 2), (5, 3), (10, 4), (12, 5), (13, 2), (14, 3), (16, 4), (17, 2), (20, 2), (22, 1)])
+def test_batch_ntt_roundtrip(gpu, b200lib, oracle, lg_n, count):
+    torch = gpu
+    rng = np.random.default_rng(7 + lg_n)
+    a = rand_elems(rng, count << lg_n, oracle)
+    d = dev(torch, a)
+    ck(b200lib.b200_batch_ntt(ptr(d), lg_n, count, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(host(d), oracle.batch_ntt(a, lg_n, count))
+    # size-independent property: iNTT(NTT(x)) == x, for every size including the largest
+    ck(b200lib.b200_batch_intt(ptr(d), lg_n, count, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(host(d), a)
+    # bit_reverse twice is the identity, once matches the oracle's permutation
+    ck(b200lib.b200_batch_bit_reverse(ptr(d), lg_n, count, None))
+    torch.cuda.synchronize()
+    ref = np.concatenate([oracle.bit_reverse(a[c << lg_n:(c + 1) << lg_n], lg_n) for c in range(count)])
+    assert np.array_equal(host(d), ref)
+
+
+@pytest.mark.parametrize("lg_n,count", [(3, 2), (8, 3), (10, 16), (11, 4), (12, 5), (13, 3), (14, 4), (16, 8), (18, 4), (20, 3)])
+def test_batch_expand_ntt(gpu, b200lib, oracle, lg_n, count):
+    torch = gpu
+    rng = np.random.default_rng(31 + lg_n)
+    a = rand_elems(rng, count << lg_n, oracle)
+    d_in = dev(torch, a)
+    d_out = torch.zeros(count << (lg_n + 2), dtype=torch.int32, device="cuda")
+    ck(b200lib.b200_batch_expand_ntt(ptr(d_out), ptr(d_in), lg_n, 2, count, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(host(d_out), oracle.batch_expand_ntt(a, lg_n, count, 2))
+
+
+@pytest.mark.parametrize("kind", EDGE)
+@pytest.mark.parametrize("lg_n", [10, 14])
+def test_ntt_edge_inputs(gpu, b200lib, oracle, kind, lg_n):
+    torch = gpu
+    count = 3
+    a = edge_input(kind, count << lg_n, oracle)
+    d = dev(torch, a)
+    ck(b200lib.b200_batch_intt(ptr(d), lg_n, count, None))
+    torch.cuda.synchronize()
+    ref = oracle.batch_intt(a, lg_n, count)
+    assert np.array_equal(host(d), ref)
+    d_out = torch.zeros(count << (lg_n + 2), dtype=torch.int32, device="cuda")
+    ck(b200lib.b200_batch_expand_ntt(ptr(d_out), ptr(d), lg_n, 2, count, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(host(d_out), oracle.batch_expand_ntt(ref, lg_n, count, 2))
+
+
+def test_intt_ntt_identity_max_size(gpu, b200lib, oracle):
+    """2^24 elements (BASELINE config 5 upper end): round trip only, the oracle is not run at this size."""
+    torch = gpu
+    lg_n = 24
+    rng = np.random.default_rng(5)
+    a = rand_elems(rng, 1 << lg_n, oracle)
+    d = dev(torch, a)
+    ck(b200lib.b200_batch_intt(ptr(d), lg_n, 1, None))
+    ck(b200lib.b200_batch_ntt(ptr(d), lg_n, 1, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(host(d), a)
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (33, 16), (256, 17), (1024, 0), (1000, 5), (4096, 32), (1 << 14, 208), (1 << 12, 64)])
+def test_poseidon2_rows(gpu, b200lib, oracle, rows, cols):
+    torch = gpu
+    rng = np.random.default_rng(rows + cols)
+    m = rand_elems(rng, max(rows * cols, 1), oracle)[: rows * cols]
+    d_m = dev(torch, m if m.size else np.zeros(1, np.uint32))
+    d_out = torch.zeros(rows * 8, dtype=torch.int32, device="cuda")
+    ck(b200lib.b200_poseidon2_rows(ptr(d_out), ptr(d_m), rows, cols, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(host(d_out), oracle.hash_rows(m, rows, cols))
+
+
+def test_poseidon2_kat_through_rows(gpu, b200lib, oracle):
+    """The permutation KAT through the product path: a 16-column row [0..16) absorbs into a zero state."""
+    torch = gpu
+    row = oracle.to_mont(np.arange(16, dtype=np.int64))
+    d_m = dev(torch, row)
+    d_out = torch.zeros(8, dtype=torch.int32, device="cuda")
+    ck(b200lib.b200_poseidon2_rows(ptr(d_out), ptr(d_m), 1, 16, None))
+    torch.cuda.synchronize()
+    st = np.zeros(24, np.uint32); st[:16] = row
+    assert np.array_equal(host(d_out), oracle.p2_mix(st)[:8])
+
+
+@pytest.mark.parametrize("n_out", [1, 2, 31, 1024, 5000])
+def test_poseidon2_fold(gpu, b200lib, oracle, n_out):
+    torch = gpu
+    rng = np.random.default_rng(n_out)
+    inp = rand_elems(rng, n_out * 16, oracle)
+    d_in = dev(torch, inp)
+    d_out = torch.zeros(n_out * 8, dtype=torch.int32, device="cuda")
+    ck(b200lib.b200_poseidon2_fold(ptr(d_out), ptr(d_in), n_out, None))
+    torch.cuda.synchronize()
+    ref = np.concatenate([oracle.hash_pair(inp[16 * i:16 * i + 8], inp[16 * i + 8:16 * i + 16]) for i in range(n_out)])
+    assert np.array_equal(host(d_out), ref)
+
+
+@pytest.mark.parametrize("lg_rows,cols", [(1, 3), (5, 16), (10, 20), (12, 64), (14, 16)])
+def test_merkle_tree(gpu, b200lib, oracle, lg_rows, cols):
+    torch = gpu
+    rows = 1 << lg_rows
+    rng = np.random.default_rng(lg_rows)
+    m = rand_elems(rng, rows * cols, oracle)
+    d_m = dev(torch, m)
+    d_nodes = torch.zeros(2 * rows * 8, dtype=torch.int32, device="cuda")
+    ck(b200lib.b200_merkle_tree(ptr(d_nodes), ptr(d_m), lg_rows, cols, None))
+    torch.cuda.synchronize()
+    ref = oracle.merkle_build(m, rows, cols)
+    assert np.array_equal(host(d_nodes)[8:], ref[8:])      # node 0 is unused
+
+
+@pytest.mark.parametrize("lg_size", [4, 8, 12, 16, 20])
+def test_fri_fold(gpu, b200lib, oracle, lg_size):
+    torch = gpu
+    size = 1 << lg_size
+    rng = np.random.default_rng(lg_size)
+    inp = rand_elems(rng, 4 * size, oracle)
+    mix = rand_elems(rng, 4, oracle)
+    d_in, d_mix = dev(torch, inp), dev(torch, mix)
+    d_out = torch.zeros(4 * (size // 16), dtype=torch.int32, device="cuda")
+    ck(b200lib.b200_fri_fold(ptr(d_out), ptr(d_in), size, ptr(d_mix), None))
+    torch.cuda.synchronize()
+    assert np.array_equal(host(d_out), oracle.fri_fold(inp, size, mix))
+
+
+@pytest.mark.parametrize("lg_n,count", [(3, 2), (10, 5), (12, 3), (13, 4), (16, 6)])
+def test_batch_evaluate_any(gpu, b200lib, oracle, lg_n, count):
+    torch = gpu
+    rng = np.random.default_rng(lg_n)
+    co = rand_elems(rng, count << lg_n, oracle)
+    x = rand_elems(rng, 4, oracle)
+    d_co, d_x = dev(torch, co), dev(torch, x)
+    d_out = torch.zeros(count * 4, dtype=torch.int32, device="cuda")
+    d_scr = torch.zeros(b200lib.b200_evaluate_scratch_words(lg_n, count), dtype=torch.int32, device="cuda")
+    ck(b200lib.b200_batch_evaluate_any(ptr(d_out), ptr(d_co), lg_n, count, ptr(d_x), ptr(d_scr), None))
+    torch.cuda.synchronize()
+    assert np.array_equal(host(d_out).reshape(count, 4), oracle.batch_evaluate_any(co, lg_n, count, x))
+
+
+def test_stream_argument(gpu, b200lib, oracle):
+    """Entry points honour the caller's stream (the agent passes its own): run on a side stream."""
+    torch = gpu
+    s = torch.cuda.Stream()
+    a = rand_elems(np.random.default_rng(1), 4 << 12, oracle)
+    d = dev(torch, a)
+    torch.cuda.synchronize()
+    ck(b200lib.b200_batch_intt(ptr(d), 12, 4, C.c_void_p(s.cuda_stream)))
+    s.synchronize()
+    assert np.array_equal(host(d), oracle.batch_intt(a, 12, 4))
