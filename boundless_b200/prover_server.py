@@ -107,6 +107,10 @@ class ProverServer:
         rw = self.opts.recursion_widths
         return Circuit(self.opts.recursion_po2, rw[0], rw[1], rw[2], kind)
 
+    def _buf(self, slot):
+        # an out-of-range slot is reported by the library ("slot out of range"), not by Python indexing
+        return self._seal_bufs[slot].ptr if 0 <= slot < len(self._seal_bufs) else self._seal_bufs[0].ptr
+
     def seal_words(self, circuit):
         return self.L.b200_seal_words(C.byref(circuit))
 
@@ -140,7 +144,7 @@ class ProverServer:
                 raise B200Error("segment trace has %d words, expected %d" % (tr.size, need))
         _lib.check(self.L.b200_prove_segment_async(self.h, slot, C.byref(c), segment.seed,
                                                     tr.ctypes.data_as(C.c_void_p) if tr is not None else None,
-                                                    self._seal_bufs[slot].ptr))
+                                                    self._buf(slot)))
         self._pending[slot] = ("segment", c, segment, tr)
 
     def submit_recursion(self, slot, kind, a, b=None):
@@ -149,7 +153,7 @@ class ProverServer:
         sb = np.ascontiguousarray(b.seal, dtype=np.uint32) if b is not None else None
         _lib.check(self.L.b200_recursion_async(self.h, slot, C.byref(c), sa.ctypes.data_as(C.c_void_p), sa.size,
                                                sb.ctypes.data_as(C.c_void_p) if sb is not None else None,
-                                               sb.size if sb is not None else 0, self._seal_bufs[slot].ptr))
+                                               sb.size if sb is not None else 0, self._buf(slot)))
         self._pending[slot] = ("recursion", c, (kind, a, b), (sa, sb))
 
     def wait(self, slot):
