@@ -1,0 +1,312 @@
+#!/usr/bin/env python3
+"""bench.py -- segments/s of the segment-proving hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]             # our arm
+    python bench.py --impl reference [--steps K] [--warmup W]       # CPU arm (oracle port of the reference path)
+    torchrun ... bench.py --gpus N ...                              # N > 1: one rank per GPU, weak scaling
+
+A step = ProverServer.prove_segment of ONE synthetic 2^20-cycle segment (BASELINE config 2: 2^20 rows x 256
+columns, blow-up 4, Poseidon2 Merkle, 50-query FRI).  `value` = segments/s with the witness expanded on the
+device (witgen stand-in inside the timed region); `e2e` = the same through the reference-facing call with the
+witness in pinned HOST memory (H2D inside the timed region) and the seal read back.  Prints ONE JSON line.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PO2 = 20
+WIDTHS = (16, 208, 32)
+CYCLES_PER_SEGMENT = 1 << PO2
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], 0.0, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def reference_arm(args):
+    """The reference's CPU path, restated (oracle port; the risc0 crates are not buildable here -- DESIGN.md).
+    Each step proves one bounded sample segment on all host threads; throughput is scaled to 2^20-row segments."""
+    from oracle import pyoracle as o
+    o.lib()
+    sample_po2 = 16
+    cores = os.cpu_count() or 1
+    for i in range(args.warmup):
+        o.prove(sample_po2 - 2, 0xB2000000 + i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        seal = o.prove(sample_po2, 0xB2000000 + i)
+    dt = time.perf_counter() - t0
+    assert o.verify(seal) == 0
+    scale = 1 << (PO2 - sample_po2)
+    sps = args.steps / (dt * scale)
+    sample = "%d x one 2^%d-row segment (same widths/protocol), time scaled x%d to 2^20 rows" % (args.steps, sample_po2, scale)
+    out = {"impl": "reference", "metric": "segments_per_sec", "value": sps, "unit": "segments/s", "n_gpus": 0, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 * scale, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+           "proved_mcycles_per_sec": sps * CYCLES_PER_SEGMENT / 1e6,
+           "config": {"workload": "synthetic 1M-cycle segment (po2=20, 16/208/32 cols, blow-up 4, 50 queries)", "po2": PO2,
+                      "parallelism": "openmp x%d" % cores},
+           "cpu_baseline": {"value": sps, "unit": "segments/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": sps, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def kernel_roofline(torch, L, pk):
+    """Dominant kernel = Poseidon2 leaf hashing of the data group (K4: 2^22 rows x 208 columns).  CUDA events on the
+    stream the kernel is launched on; algorithmic bytes = 16*W*N + 128*N."""
+    rows, cols = 1 << (PO2 + 2), WIDTHS[1]
+    m = torch.randint(0, 2013265921, (cols * rows,), dtype=torch.int32, device="cuda")
+    out = torch.empty(rows * 8, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream()
+    sp = C.c_void_p(st.cuda_stream)
+    for _ in range(2):
+        assert L.b200_poseidon2_rows(C.c_void_p(out.data_ptr()), C.c_void_p(m.data_ptr()), rows, cols, sp) is None
+    evs = []
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        assert L.b200_poseidon2_rows(C.c_void_p(out.data_ptr()), C.c_void_p(m.data_ptr()), rows, cols, sp) is None
+        b.record(st)
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+    alg_bytes = rows * cols * 4 + rows * 32
+    perms = rows * ((cols + 15) // 16)
+    ach = alg_bytes / (ms * 1e-3) / 1e9
+    roof = {"kernel": "k_p2_rows (K4, data group 2^22 x 208)", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": ach / pk["hbm_gbs"], "traffic": None, "ms_per_launch": ms, "alg_bytes_per_launch": alg_bytes}
+    # the honest bound for this kernel is the INT32 pipe (SURVEY finding 8): report it beside the HBM figure
+    gmul = perms * 1356 / (ms * 1e-3) / 1e9
+    INT_PEAK = 3508.0   # Gmulmod/s, independent-chain Montgomery microbenchmark on this part (profiles/microbench_r01.txt)
+    roof_int = {"kernel": roof["kernel"], "bound": "int32", "achieved": gmul, "peak": INT_PEAK, "unit": "Gmulmod/s",
+                "frac": gmul / INT_PEAK, "gperm_per_s": perms / (ms * 1e-3) / 1e9}
+    del m, out
+    # NTT kernels (HBM-bound): expand+NTT of 16 columns 2^20 -> 2^22, and iNTT of 16 x 2^20
+    n, cnt = PO2, 16
+    a_in = torch.randint(0, 2013265921, (cnt << n,), dtype=torch.int32, device="cuda")
+    a_out = torch.empty(cnt << (n + 2), dtype=torch.int32, device="cuda")
+    def timeit(fn):
+        fn(); fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        for _ in range(3):
+            fn()
+        b.record(st); torch.cuda.synchronize()
+        return a.elapsed_time(b) / 3
+    ms_e = timeit(lambda: L.b200_batch_expand_ntt(C.c_void_p(a_out.data_ptr()), C.c_void_p(a_in.data_ptr()), n, 2, cnt, sp))
+    ms_i = timeit(lambda: L.b200_batch_intt(C.c_void_p(a_in.data_ptr()), n, cnt, sp))
+    kernels = [
+        {"kernel": "expand+NTT 16 x 2^20 -> 2^22 (K3)", "ms": ms_e, "alg_gbs": 20.0 * cnt * (1 << n) / (ms_e * 1e-3) / 1e9},
+        {"kernel": "iNTT 16 x 2^20 (K1)", "ms": ms_i, "alg_gbs": 8.0 * cnt * (1 << n) / (ms_i * 1e-3) / 1e9},
+    ]
+    for k in kernels:
+        k["frac_of_hbm_peak"] = k["alg_gbs"] / pk["hbm_gbs"]
+    return roof, roof_int, kernels
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--slots", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from boundless_b200 import ProverOpts, Segment, get_prover_server
+    from boundless_b200 import lib as b200lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pk, pk_kind = peaks()
+    L = b200lib.require_gpu(local_rank)
+    slots = max(1, args.slots)
+    srv = get_prover_server(ProverOpts(segment_po2=PO2, segment_widths=WIDTHS, slots=slots, device=local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(n_steps, traces=None, first_index=0):
+        """n_steps segments through the public API, `slots` in flight; returns (wall_s, device_ms)."""
+        inflight = []
+        t0 = time.perf_counter()
+        L.b200_prover_mark(srv.h, 0, 0)
+        for i in range(n_steps):
+            slot = i % slots
+            if len(inflight) == slots:
+                srv.wait(inflight.pop(0))
+            idx = rank * 1000003 + first_index + i
+            seg = Segment(index=idx, po2=PO2, trace=None if traces is None else traces[i % len(traces)][1],
+                          seed=None if traces is None else traces[i % len(traces)][0])
+            srv.submit_segment(slot, seg)
+            L.b200_prover_mark(srv.h, slot, 1)          # end mark of this slot (overwritten by its next proof)
+            inflight.append(slot)
+        rec = None
+        for s in inflight:
+            rec = srv.wait(s)
+        wall = time.perf_counter() - t0
+        dev_ms = max(L.b200_prover_marks_ms(srv.h, 0, 0, s, 1) for s in range(min(slots, n_steps)))
+        return wall, dev_ms, rec
+
+    # ---- device-resident arm (value) ----
+    run(args.warmup, first_index=0)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.b200_kernel_launches()
+    barrier()
+    wall, dev_ms, rec = run(args.steps, first_index=100)
+    barrier()
+    launches = L.b200_kernel_launches() - launches0
+    clocks = sampler.stop()
+    t = torch.tensor([wall, dev_ms / 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall_max, dev_max = float(t[0]), float(t[1])
+    # slots overlap, so the device span of the whole loop is the honest per-rank time; wall (sync to sync) bounds it
+    sec = max(dev_max, 1e-9)
+    value = world * args.steps / sec
+
+    # ---- end-to-end arm: witness in pinned host memory, H2D inside the timed region, seal D2H ----
+    c = srv.seg_circuit
+    tw = (c.w_code + c.w_data) << c.po2
+    ntr = 2
+    pinned = []
+    for k in range(ntr):
+        p = C.c_void_p()
+        b200lib.check(L.b200_host_alloc(C.byref(p), tw * 4))
+        arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(tw,))
+        seed = 0xB2000000 + rank * 1000003 + 500 + k
+        b200lib.check(L.b200_witgen_to_host(srv.h, 0, C.byref(c), seed, p))
+        pinned.append((seed, arr, p))
+    traces = [(s, a) for s, a, _ in pinned]
+    run(min(args.warmup, 2), traces=traces)
+    barrier()
+    wall_e, dev_e, rec_e = run(args.steps, traces=traces)
+    barrier()
+    te = torch.tensor([wall_e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / float(te[0])      # wall clock sync-to-sync: includes H2D, launches, D2H
+    seal_bytes = int(rec_e.seal.size * 4)
+
+    out = None
+    if rank == 0:
+        roof, roof_int, kernels = kernel_roofline(torch, L, pk)
+        roof["peak_source"] = pk_kind + " (MEASURED_PEAKS.json hbm_gbs)" if pk_kind == "measured" else "fallback 6650 GB/s"
+        out = {
+            "metric": "segments_per_sec", "value": value, "unit": "segments/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "proved_mcycles_per_sec": value * CYCLES_PER_SEGMENT / 1e6,
+            "config": {"workload": "synthetic 1M-cycle segment (po2=20, 16/208/32 cols + 16 check, blow-up 4, 50 queries) x %d per GPU" % args.steps,
+                       "po2": PO2, "widths": list(WIDTHS), "slots_in_flight": slots, "parallelism": "segment-per-GPU x%d" % world,
+                       "l2_policy": "per-step working set ~6.9 GB >> 126 MB L2 (inputs larger than L2)",
+                       "witgen_standin_in_timed_region": True, "timer": "CUDA events first-launch -> last-op, max over ranks",
+                       "wall_s_sync_to_sync": wall_max},
+            "e2e": {"value": e2e_value, "unit": "segments/s", "h2d_bytes_per_step": tw * 4, "d2h_bytes_per_step": seal_bytes,
+                    "timer": "wall clock, sync to sync, max over ranks", "api": "ProverServer.submit_segment/wait (host trace, pinned)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof, "roofline_int32": roof_int, "kernels": kernels,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import pyoracle as o          # checker / CPU baseline leg only
+            o.lib()
+            sample_po2 = 16
+            o.prove(12, 1)
+            t0 = time.perf_counter()
+            seal = o.prove(sample_po2, 0xB2000000)
+            dt = time.perf_counter() - t0
+            scale = 1 << (PO2 - sample_po2)
+            out["cpu_baseline"] = {"value": 1.0 / (dt * scale), "unit": "segments/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": "one 2^%d-row segment (same widths/protocol) on all host threads, time scaled x%d" % (sample_po2, scale),
+                                   "sample_seconds": dt, "verifies": o.verify(seal) == 0}
+        print(json.dumps(out))
+    for _, _, p in pinned:
+        L.b200_host_free(p)
+    srv.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -81,7 +81,7 @@ struct Arena {
 
 struct Slot {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_mark[2] = {nullptr, nullptr};
     Arena arena;
     // fixed regions (sized for the max circuit)
     uint32_t *coeffs, *evals, *check_coeffs, *check_evals, *nodes[4];
@@ -321,6 +321,7 @@ void b200_prover_destroy(b200_prover* p) {
         if (s.h_stage) cudaFreeHost(s.h_stage);
         if (s.ev_begin) cudaEventDestroy(s.ev_begin);
         if (s.ev_end) cudaEventDestroy(s.ev_end);
+        for (int i = 0; i < 2; i++) if (s.ev_mark[i]) cudaEventDestroy(s.ev_mark[i]);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     delete p;
@@ -387,6 +388,34 @@ float b200_prover_last_ms(b200_prover* p, uint32_t slot) {
     float ms = -1.f;
     if (cudaEventElapsedTime(&ms, p->slots[slot].ev_begin, p->slots[slot].ev_end) != cudaSuccess) return -1.f;
     return ms;
+}
+
+const char* b200_prover_mark(b200_prover* p, uint32_t slot, uint32_t which) {
+    if (!p || slot >= p->slots.size() || which > 1) { set_error("b200: bad prover/slot/mark"); return last_error(); }
+    CU(cudaSetDevice(p->device));
+    Slot& s = p->slots[slot];
+    if (!s.ev_mark[which]) CU(cudaEventCreate(&s.ev_mark[which]));
+    CU(cudaEventRecord(s.ev_mark[which], s.stream));
+    return nullptr;
+}
+float b200_prover_marks_ms(b200_prover* p, uint32_t slot_a, uint32_t which_a, uint32_t slot_b, uint32_t which_b) {
+    if (!p || slot_a >= p->slots.size() || slot_b >= p->slots.size() || which_a > 1 || which_b > 1) return -1.f;
+    cudaEvent_t a = p->slots[slot_a].ev_mark[which_a], b = p->slots[slot_b].ev_mark[which_b];
+    float ms = -1.f;
+    if (!a || !b || cudaEventSynchronize(b) != cudaSuccess || cudaEventElapsedTime(&ms, a, b) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+const char* b200_witgen_to_host(b200_prover* p, uint32_t slot, const b200_circuit* c, uint64_t seed, uint32_t* h_trace) {
+    const char* e = slot_check(p, slot, c);
+    if (e) return e;
+    if (!h_trace) { set_error("b200: null h_trace"); return last_error(); }
+    Slot& s = p->slots[slot];
+    const size_t tw = (size_t)(c->w_code + c->w_data) << c->po2;
+    KL(launch_gen_trace(s.coeffs, seed, nullptr, tw, s.stream));
+    CU(cudaMemcpyAsync(h_trace, s.coeffs, tw * 4, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    return nullptr;
 }
 
 const char* b200_host_alloc(void** out, size_t bytes) {

@@ -52,6 +52,9 @@ SYMBOLS = {
     "b200_recursion_async": (_cp, [_vp, _u32, C.POINTER(Circuit), _vp, _sz, _vp, _sz, _vp]),
     "b200_prover_wait": (_cp, [_vp, _u32]),
     "b200_prover_last_ms": (C.c_float, [_vp, _u32]),
+    "b200_prover_mark": (_cp, [_vp, _u32, _u32]),
+    "b200_prover_marks_ms": (C.c_float, [_vp, _u32, _u32, _u32, _u32]),
+    "b200_witgen_to_host": (_cp, [_vp, _u32, C.POINTER(Circuit), _u64, _vp]),
     "b200_kernel_launches": (_u64, []),
     "b200_host_alloc": (_cp, [C.POINTER(_vp), _sz]),
     "b200_host_free": (None, [_vp]),

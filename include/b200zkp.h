@@ -91,6 +91,11 @@ const char* b200_recursion_async(b200_prover* p, uint32_t slot, const b200_circu
 const char* b200_prover_wait(b200_prover* p, uint32_t slot);
 /* device time (ms) between the first and last operation of the slot's last proof */
 float b200_prover_last_ms(b200_prover* p, uint32_t slot);
+/* timing marks: record event `which` (0/1) on the slot's stream; elapsed ms between two marks (-1 if unset) */
+const char* b200_prover_mark(b200_prover* p, uint32_t slot, uint32_t which);
+float b200_prover_marks_ms(b200_prover* p, uint32_t slot_a, uint32_t which_a, uint32_t slot_b, uint32_t which_b);
+/* witgen stand-in: expand `seed` into the (w_code + w_data) x 2^po2 witness and copy it to host memory (synchronous) */
+const char* b200_witgen_to_host(b200_prover* p, uint32_t slot, const b200_circuit* c, uint64_t seed, uint32_t* h_trace);
 /* number of kernels this library launched since load (all threads) */
 uint64_t b200_kernel_launches(void);
 /* host-pinned allocation helpers for h_trace / h_seal */
