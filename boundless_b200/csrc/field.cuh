@@ -5,8 +5,11 @@
 // Representation is identical to the reference's: u32 Montgomery form a*2^32 mod p, canonical in [0,p),
 // so buffers are interchangeable with a risc0 `DeviceBuffer<BabyBearElem>` (SURVEY.md 8b "Data layout").
 //
-// Instruction budget (checked with cuobjdump -sass): mul = IMAD.WIDE.U32 + IMAD + IMAD.HI.U32 + IADD + VIADDMNMX.U32,
-// add/sub = IADD + VIADDMNMX.U32 (the DPX fused add-min removes the compare/select pair).
+// B200 pipe model (measured, profiles/microbench_r01.txt + ncu): every integer multiply (IMAD 2 cyc, IMAD.HI /
+// IMAD.WIDE 4 cyc per warp per SMSP) runs on the single "fmaheavy" pipe, which is what saturates in the Poseidon2 and
+// NTT kernels; plain adds that ptxas encodes as IMAD.IADD land on that pipe too.  So: a multiply is exactly
+// IMAD.WIDE + IMAD + IMAD.HI (10 fmaheavy cycles) and every add/sub/correction is written with the DPX fused
+// add-min (VIADDMNMX, ALU pipe), which ptxas cannot turn into an IMAD.
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
@@ -23,22 +26,22 @@ constexpr uint32_t NBETA_M = 1073741848u;  // mont(p - 11): X^4 = -11
 __device__ __forceinline__ uint32_t addmin(uint32_t x, uint32_t y, uint32_t z) { return __viaddmin_u32(x, y, z); }
 
 __device__ __forceinline__ uint32_t fp_add(uint32_t a, uint32_t b) {
-    uint32_t s = a + b;                     // < 2p < 2^32
+    uint32_t s = addmin(a, b, 0xffffffffu); // a + b (< 2p < 2^32) on the ALU pipe
     return addmin(s, 0u - P, s);            // min(s - p, s): s - p wraps high when s < p
 }
 __device__ __forceinline__ uint32_t fp_sub(uint32_t a, uint32_t b) {
-    uint32_t d = a - b;                     // wraps high when a < b
-    return addmin(d, P, d);                 // min(d + p, d)
+    uint32_t d = addmin(a, P, 0xffffffffu) - b;   // a + p - b in (0, 2p)
+    return addmin(d, 0u - P, d);            // min(d - p, d)
 }
 __device__ __forceinline__ uint32_t fp_neg(uint32_t a) { return a ? P - a : 0u; }
 __device__ __forceinline__ uint32_t fp_dbl(uint32_t a) { return fp_add(a, a); }
 
 // Montgomery reduction of T < p*2^32 given as (hi, lo): returns T / 2^32 mod p, canonical.
 __device__ __forceinline__ uint32_t fp_redc(uint32_t hi, uint32_t lo) {
-    uint32_t m = lo * PINV;                 // m*p == lo (mod 2^32)
-    uint32_t t = __umulhi(m, P);            // (T - m*p) / 2^32 = hi - t, in (-p, p)
-    uint32_t r = hi - t;
-    return addmin(r, P, r);                 // min(r + p, r)
+    uint32_t m = lo * (0u - PINV);          // m*p == -lo (mod 2^32)
+    uint64_t o2 = (uint64_t)m * P + (((uint64_t)hi << 32) | lo);   // IMAD.HI(m, P, lo) + hi; low word cancels
+    uint32_t r = (uint32_t)(o2 >> 32);      // (T + m*p) / 2^32 in [0, 2p)
+    return addmin(r, 0u - P, r);            // min(r - p, r)
 }
 __device__ __forceinline__ uint32_t fp_mul(uint32_t a, uint32_t b) {
     uint64_t o = (uint64_t)a * b;

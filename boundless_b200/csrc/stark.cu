@@ -28,7 +28,8 @@ __global__ void k_gen_trace(uint32_t* __restrict__ out, uint64_t seed, uint64_t 
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     z ^= z >> 31;
-    out[i] = fp_to_mont((uint32_t)(z % P));
+    // mont(z mod p) = hi*2^64 + lo*2^32 (mod p) = hi * R3 / R + lo * R2 / R, with R2 = 2^64, R3 = 2^96 (mod p)
+    out[i] = fp_add(fp_mul((uint32_t)(z >> 32), 317946875u), fp_mul((uint32_t)z, R2));
 }
 cudaError_t launch_gen_trace(uint32_t* d_out, uint64_t seed, const uint32_t* d_seed_words, uint64_t count, cudaStream_t s) {
     if (!count) return cudaSuccess;
