@@ -25,23 +25,51 @@ constexpr uint32_t NBETA_M = 1073741848u;  // mont(p - 11): X^4 = -11
 // min(x + y, z) as one VIADDMNMX on sm_90+/sm_100
 __device__ __forceinline__ uint32_t addmin(uint32_t x, uint32_t y, uint32_t z) { return __viaddmin_u32(x, y, z); }
 
+// Build-time variants (tools/microbench.cu measures them; the defaults are the fastest measured on B200).
+#ifndef B200_ADD_V
+#define B200_ADD_V 0
+#endif
+#ifndef B200_REDC_V
+#define B200_REDC_V 0
+#endif
 __device__ __forceinline__ uint32_t fp_add(uint32_t a, uint32_t b) {
-    uint32_t s = addmin(a, b, 0xffffffffu); // a + b (< 2p < 2^32) on the ALU pipe
+#if B200_ADD_V == 0
+    uint32_t s = a + b;                     // < 2p < 2^32
+#else
+    uint32_t s = addmin(a, b, 0xffffffffu); // same sum, forced onto the ALU pipe
+#endif
     return addmin(s, 0u - P, s);            // min(s - p, s): s - p wraps high when s < p
 }
 __device__ __forceinline__ uint32_t fp_sub(uint32_t a, uint32_t b) {
+#if B200_ADD_V == 0
+    uint32_t d = a - b;                     // wraps high when a < b
+    return addmin(d, P, d);                 // min(d + p, d)
+#else
     uint32_t d = addmin(a, P, 0xffffffffu) - b;   // a + p - b in (0, 2p)
     return addmin(d, 0u - P, d);            // min(d - p, d)
+#endif
 }
 __device__ __forceinline__ uint32_t fp_neg(uint32_t a) { return a ? P - a : 0u; }
 __device__ __forceinline__ uint32_t fp_dbl(uint32_t a) { return fp_add(a, a); }
 
 // Montgomery reduction of T < p*2^32 given as (hi, lo): returns T / 2^32 mod p, canonical.
 __device__ __forceinline__ uint32_t fp_redc(uint32_t hi, uint32_t lo) {
+#if B200_REDC_V == 0
+    uint32_t m = lo * PINV;                 // m*p == lo (mod 2^32)
+    uint32_t t = __umulhi(m, P);            // (T - m*p) / 2^32 = hi - t, in (-p, p)
+    uint32_t r = hi - t;
+    return addmin(r, P, r);                 // min(r + p, r)
+#elif B200_REDC_V == 1
     uint32_t m = lo * (0u - PINV);          // m*p == -lo (mod 2^32)
     uint64_t o2 = (uint64_t)m * P + (((uint64_t)hi << 32) | lo);   // IMAD.HI(m, P, lo) + hi; low word cancels
     uint32_t r = (uint32_t)(o2 >> 32);      // (T + m*p) / 2^32 in [0, 2p)
     return addmin(r, 0u - P, r);            // min(r - p, r)
+#else
+    uint32_t m = lo + ((lo + (lo << 4)) << 27);   // lo * 0x88000001 with two LEAs (ALU pipe) instead of an IMAD
+    uint32_t t = __umulhi(m, P);
+    uint32_t r = hi - t;
+    return addmin(r, P, r);
+#endif
 }
 __device__ __forceinline__ uint32_t fp_mul(uint32_t a, uint32_t b) {
     uint64_t o = (uint64_t)a * b;

@@ -19,6 +19,7 @@
 // in shared memory, inter-pass twiddles from a two-table decomposition w^e = lo[e & mask] * hi[e >> h].
 #include "internal.h"
 #include "field.cuh"
+#include <cstdlib>
 
 namespace b200 {
 
@@ -204,6 +205,176 @@ __global__ void __launch_bounds__(256) k_ntt_contig(uint32_t* __restrict__ out, 
     }
 }
 
+
+// =========================================================================================================
+// Specialised (compile-time size) passes: all stage strides, twiddle offsets and loop counts are immediates,
+// tables are read through the read-only path (L1-resident, no per-CTA staging), so a CTA only stages its data tile.
+// =========================================================================================================
+template <int K, int LB, bool DIF, typename ADDR>
+__device__ __forceinline__ void ntt_stage_c(uint32_t* s, const uint32_t* __restrict__ tw, uint32_t gidx, ADDR addr) {
+    constexpr int R = 1 << K;
+    constexpr uint32_t q = (1u << LB) >> K;
+    const uint32_t b = gidx >> (LB - K), o = gidx & (q - 1);
+    const uint32_t base = (b << LB) + o;
+    uint32_t x[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) x[j] = s[addr(base + j * q)];
+    const uint32_t* twp = tw + o;
+#pragma unroll
+    for (int ll = 0; ll < K; ll++) {
+        const int l = DIF ? ll : (K - 1 - ll);
+        const int half = R >> (l + 1);
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            if ((j & half) == 0) {
+                const uint32_t w = __ldg(twp + ((1u << LB) >> (l + 1)) + (j & (half - 1)) * q);
+                const uint32_t a = x[j], bb = x[j + half];
+                if (DIF) {
+                    x[j] = fp_add(a, bb);
+                    x[j + half] = fp_mul(fp_sub(a, bb), w);
+                } else {
+                    const uint32_t t = fp_mul(bb, w);
+                    x[j] = fp_add(a, t);
+                    x[j + half] = fp_sub(a, t);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < R; j++) s[addr(base + j * q)] = x[j];
+}
+
+// runs all stages of a length-2^LOGL transform held in shared memory; LOW = number of already-done low levels (DIT expand)
+template <int LOGL, int LOW, bool DIF, int DONE = 0>
+struct NttStages {
+    template <typename MK>
+    static __device__ __forceinline__ void run(uint32_t* s, const uint32_t* tw, uint32_t tid, uint32_t nth, uint32_t nbatch_shift, MK mk) {
+        constexpr int REM = LOGL - LOW - DONE;
+        if constexpr (REM > 0) {
+            // DIT takes the remainder stage first (next to the expand), DIF takes it last
+            constexpr int K = DIF ? (REM >= 4 ? 4 : REM) : ((REM % 4) ? (REM % 4) : 4);
+            constexpr int LB = DIF ? (LOGL - DONE) : (LOW + DONE + K);
+            const uint32_t total = ((1u << LOGL) >> K) << nbatch_shift;
+            for (uint32_t w = tid; w < total; w += nth) ntt_stage_c<K, LB, DIF>(s, tw, mk.gidx(w), mk.addr(w));
+            __syncthreads();
+            NttStages<LOGL, LOW, DIF, DONE + K>::run(s, tw, tid, nth, nbatch_shift, mk);
+        }
+    }
+};
+
+struct MkStrided {      // work item w -> (group index, column t)
+    uint32_t lgTW;
+    __device__ __forceinline__ uint32_t gidx(uint32_t w) const { return w >> lgTW; }
+    __device__ __forceinline__ AddrStrided addr(uint32_t w) const { return AddrStrided{lgTW, w & ((1u << lgTW) - 1)}; }
+};
+template <int LOGL, bool DIF>
+__global__ void __launch_bounds__(512) k_ntt_strided_c(uint32_t* __restrict__ data, uint32_t lgTW, uint32_t row_stride, uint32_t tiles_per_poly,
+                                                       size_t poly_stride, const uint32_t* __restrict__ tw_g,
+                                                       const uint32_t* __restrict__ pow_g, uint32_t lg_m) {
+    extern __shared__ uint32_t smem[];
+    constexpr uint32_t L = 1u << LOGL;
+    const uint32_t TW = 1u << lgTW;
+    uint32_t* tile = smem;
+    const uint32_t tid = threadIdx.x, nth = blockDim.x;
+    const uint32_t poly = blockIdx.x / tiles_per_poly, tcol = blockIdx.x % tiles_per_poly;
+    uint32_t* g = data + (size_t)poly * poly_stride + ((size_t)tcol << lgTW);
+    const uint32_t c = tid & (TW - 1), r0 = tid >> lgTW, rstep = nth >> lgTW;
+    {
+        const uint32_t* gp = g + (size_t)r0 * row_stride + c;
+        const size_t gstep = (size_t)rstep * row_stride;
+        uint32_t* tp = tile + (r0 << lgTW) + c;
+#pragma unroll 16
+        for (uint32_t r = r0; r < L; r += rstep) { *tp = __ldg(gp); gp += gstep; tp += rstep << lgTW; }
+    }
+    __syncthreads();
+    NttStages<LOGL, 0, DIF>::run(tile, tw_g, tid, nth, lgTW, MkStrided{lgTW});
+    if (pow_g) {
+        const uint32_t h = (lg_m + 1) / 2;
+        PowTab pt{pow_g, pow_g + (1u << h), h, (1u << h) - 1};
+        const uint32_t mmask = (1u << lg_m) - 1, col = (tcol << lgTW) + c;
+        uint32_t* gp = g + (size_t)r0 * row_stride + c;
+        const size_t gstep = (size_t)rstep * row_stride;
+        const uint32_t* tp = tile + (r0 << lgTW) + c;
+        for (uint32_t r = r0; r < L; r += rstep) {
+            const uint32_t e = (col * bitrev(r, LOGL)) & mmask;
+            *gp = fp_mul(*tp, fp_mul(__ldg(pt.lo + (e & pt.mask)), __ldg(pt.hi + (e >> h))));
+            gp += gstep; tp += rstep << lgTW;
+        }
+    } else {
+        uint32_t* gp = g + (size_t)r0 * row_stride + c;
+        const size_t gstep = (size_t)rstep * row_stride;
+        const uint32_t* tp = tile + (r0 << lgTW) + c;
+#pragma unroll 8
+        for (uint32_t r = r0; r < L; r += rstep) { *gp = *tp; gp += gstep; tp += rstep << lgTW; }
+    }
+}
+
+// contiguous rows (rows_per_poly is a power of two: poly = R >> lg_rpp)
+template <int LOGLC, int LGE, bool DIF>
+__global__ void __launch_bounds__(256) k_ntt_contig_c(uint32_t* out, const uint32_t* in, uint32_t rows_per_cta, uint32_t lg_rpp,
+                                                      uint32_t total_rows, size_t in_poly_stride, size_t out_poly_stride,
+                                                      const uint32_t* __restrict__ tw_g, const uint32_t* __restrict__ pow_g,
+                                                      uint32_t lg_m, uint32_t lg_rows, uint32_t scale) {
+    extern __shared__ uint32_t smem[];
+    constexpr uint32_t Lc = 1u << LOGLC, Lin = Lc >> LGE, rowpad = Lc + (Lc >> 4);
+    uint32_t* tile = smem;
+    const uint32_t tid = threadIdx.x, nth = blockDim.x;
+    const uint32_t row0 = blockIdx.x * rows_per_cta;
+    const uint32_t rpp_mask = (1u << lg_rpp) - 1;
+    for (uint32_t rr = 0; rr < rows_per_cta; rr++) {
+        const uint32_t R = row0 + rr;
+        if (R >= total_rows) break;
+        const uint32_t* src = in + (size_t)(R >> lg_rpp) * in_poly_stride + (size_t)(R & rpp_mask) * Lin;
+        uint32_t* trow = tile + rr * rowpad;
+        for (uint32_t k = tid; k < Lin; k += nth) {
+            const uint32_t v = src[k], pp = k << LGE, ph = pp + (pp >> 4);     // replicas stay inside one 16-word pad group
+#pragma unroll
+            for (uint32_t e = 0; e < (1u << LGE); e++) trow[ph + e] = v;
+        }
+    }
+    __syncthreads();
+    constexpr int NLEV = LOGLC - LGE;
+    if constexpr (DIF) {
+        constexpr int K1 = NLEV >= 4 ? 4 : NLEV, K2 = (NLEV - K1) >= 4 ? 4 : (NLEV - K1), K3 = (NLEV - K1 - K2) >= 4 ? 4 : (NLEV - K1 - K2),
+                      K4 = NLEV - K1 - K2 - K3;
+        static_assert(K4 <= 4, "row too long");
+        if constexpr (K1 > 0) { for (uint32_t w = tid; w < rows_per_cta << (LOGLC - K1); w += nth) ntt_stage_c<K1, LOGLC, true>(tile, tw_g, w & ((1u << (LOGLC - K1)) - 1), AddrContig{(w >> (LOGLC - K1)) * rowpad}); __syncthreads(); }
+        if constexpr (K2 > 0) { for (uint32_t w = tid; w < rows_per_cta << (LOGLC - K2); w += nth) ntt_stage_c<K2, LOGLC - K1, true>(tile, tw_g, w & ((1u << (LOGLC - K2)) - 1), AddrContig{(w >> (LOGLC - K2)) * rowpad}); __syncthreads(); }
+        if constexpr (K3 > 0) { for (uint32_t w = tid; w < rows_per_cta << (LOGLC - K3); w += nth) ntt_stage_c<K3, LOGLC - K1 - K2, true>(tile, tw_g, w & ((1u << (LOGLC - K3)) - 1), AddrContig{(w >> (LOGLC - K3)) * rowpad}); __syncthreads(); }
+        if constexpr (K4 > 0) { for (uint32_t w = tid; w < rows_per_cta << (LOGLC - K4); w += nth) ntt_stage_c<K4, LOGLC - K1 - K2 - K3, true>(tile, tw_g, w & ((1u << (LOGLC - K4)) - 1), AddrContig{(w >> (LOGLC - K4)) * rowpad}); __syncthreads(); }
+    } else {
+        constexpr int K1 = (NLEV % 4) ? (NLEV % 4) : (NLEV >= 4 ? 4 : 0), K2 = (NLEV - K1) >= 4 ? 4 : 0, K3 = (NLEV - K1 - K2) >= 4 ? 4 : 0,
+                      K4 = NLEV - K1 - K2 - K3;
+        static_assert(K4 == 0 || K4 == 4, "row too long");
+        if constexpr (K1 > 0) { for (uint32_t w = tid; w < rows_per_cta << (LOGLC - K1); w += nth) ntt_stage_c<K1, LGE + K1, false>(tile, tw_g, w & ((1u << (LOGLC - K1)) - 1), AddrContig{(w >> (LOGLC - K1)) * rowpad}); __syncthreads(); }
+        if constexpr (K2 > 0) { for (uint32_t w = tid; w < rows_per_cta << (LOGLC - K2); w += nth) ntt_stage_c<K2, LGE + K1 + K2, false>(tile, tw_g, w & ((1u << (LOGLC - K2)) - 1), AddrContig{(w >> (LOGLC - K2)) * rowpad}); __syncthreads(); }
+        if constexpr (K3 > 0) { for (uint32_t w = tid; w < rows_per_cta << (LOGLC - K3); w += nth) ntt_stage_c<K3, LGE + K1 + K2 + K3, false>(tile, tw_g, w & ((1u << (LOGLC - K3)) - 1), AddrContig{(w >> (LOGLC - K3)) * rowpad}); __syncthreads(); }
+        if constexpr (K4 > 0) { for (uint32_t w = tid; w < rows_per_cta << (LOGLC - K4); w += nth) ntt_stage_c<K4, LGE + K1 + K2 + K3 + K4, false>(tile, tw_g, w & ((1u << (LOGLC - K4)) - 1), AddrContig{(w >> (LOGLC - K4)) * rowpad}); __syncthreads(); }
+    }
+    const uint32_t h = (lg_m + 1) / 2;
+    const uint32_t* plo = pow_g; const uint32_t* phi = pow_g + (1u << h);
+    const uint32_t lmask = (1u << h) - 1, mmask = (1u << lg_m) - 1;
+    for (uint32_t rr = 0; rr < rows_per_cta; rr++) {
+        const uint32_t R = row0 + rr;
+        if (R >= total_rows) break;
+        const uint32_t rho = R & rpp_mask;
+        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(R >> lg_rpp) * out_poly_stride + (size_t)rho * Lc);
+        const uint32_t* trow = tile + rr * rowpad;
+        const uint32_t d1 = bitrev(rho, lg_rows);
+        for (uint32_t k4 = tid; k4 < Lc / 4; k4 += nth) {
+            const uint32_t k = k4 * 4, ph = k + (k >> 4);
+            uint32_t v[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                v[i] = trow[ph + i];
+                if (pow_g) { const uint32_t e = ((k + i) * d1) & mmask; v[i] = fp_mul(v[i], fp_mul(__ldg(plo + (e & lmask)), __ldg(phi + (e >> h)))); }
+                else if (scale) v[i] = fp_mul(v[i], scale);
+            }
+            dst[k4] = make_uint4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
 __global__ void k_zk_shift(uint32_t* __restrict__ io, uint32_t lg_n, size_t total, const uint32_t* __restrict__ p3lo,
                            const uint32_t* __restrict__ p3hi) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -221,9 +392,13 @@ __global__ void k_bit_reverse(uint32_t* __restrict__ io, uint32_t lg_n, size_t t
 }
 
 // ---- host launchers ------------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
 static uint32_t strided_lgTW(uint32_t logL) {
-    // target 64 KB tiles, at least 8 columns (32-byte runs), at most 32
-    uint32_t lg = logL >= 14 ? 3 : (14 - logL);
+    const int ov = env_int("B200_NTT_LGTW", -1);        // tuning override (tools/time_ntt.py)
+    if (ov >= 2 && ov <= 5) return (uint32_t)ov;
+    // 32 KB tiles (4-6 CTAs of 256 threads per SM hide the tile-load latency; measured best on B200 with
+    // tools/time_ntt.py), at least 8 columns (32-byte sectors), at most 32
+    uint32_t lg = logL >= 13 ? 3 : (13 - logL);
     if (lg > 5) lg = 5;
     if (lg < 3) lg = 3;
     return lg;
@@ -238,11 +413,19 @@ static cudaError_t run_strided(const DeviceTables* T, uint32_t* d, uint32_t logL
     const uint32_t tiles_per_poly = ncols >> lgTW;
     const uint32_t h = (lg_m + 1) / 2;
     size_t smem = ((size_t)(1u << logL) << lgTW) * 4 + ((size_t)4 << logL) + (pow_g ? ((size_t)4 << h) + ((size_t)4 << (lg_m - h)) : 0);
+    const uint32_t* twt = DIF ? T->tw_inv : T->tw_fwd;
+    if (logL >= 6 && logL <= 11) {
+        const size_t sm = ((size_t)(1u << logL) << lgTW) * 4;
+#define B200_STRIDED_CASE(LL) case LL: { auto kc = k_ntt_strided_c<LL, DIF>; \
+            cudaError_t e = cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
+            kc<<<tiles_per_poly * count, env_int("B200_NTT_THREADS", 256), sm, s>>>(d, lgTW, row_stride, tiles_per_poly, poly_stride, twt, pow_g, lg_m); return cudaGetLastError(); }
+        switch (logL) { B200_STRIDED_CASE(6) B200_STRIDED_CASE(7) B200_STRIDED_CASE(8) B200_STRIDED_CASE(9) B200_STRIDED_CASE(10) B200_STRIDED_CASE(11) default: break; }
+#undef B200_STRIDED_CASE
+    }
     auto kern = k_ntt_strided<DIF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<tiles_per_poly * count, 512, smem, s>>>(d, logL, lgTW, row_stride, tiles_per_poly, poly_stride,
-                                                    DIF ? T->tw_inv : T->tw_fwd, pow_g, lg_m);
+    kern<<<tiles_per_poly * count, 512, smem, s>>>(d, logL, lgTW, row_stride, tiles_per_poly, poly_stride, twt, pow_g, lg_m);
     return cudaGetLastError();
 }
 
@@ -256,12 +439,23 @@ static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32
     const uint32_t h = (lg_m + 1) / 2;
     const uint32_t Lc = 1u << logLc;
     size_t smem = (size_t)rpc * (Lc + (Lc >> 4)) * 4 + (size_t)Lc * 4 + (pow_g ? ((size_t)4 << h) + ((size_t)4 << (lg_m - h)) : 0);
+    const uint32_t grid = (uint32_t)((total_rows + rpc - 1) / rpc);
+    const uint32_t* twt = DIF ? T->tw_inv : T->tw_fwd;
+    uint32_t lg_rpp = 0; while ((1u << lg_rpp) < rows_per_poly) lg_rpp++;
+    if (logLc >= 8 && logLc <= 13 && (DIF ? lg_e == 0 : lg_e == 2) && (1u << lg_rpp) == rows_per_poly) {
+        const size_t sm = (size_t)rpc * (Lc + (Lc >> 4)) * 4;
+#define B200_CONTIG_CASE(LL) case LL: { auto kc = k_ntt_contig_c<LL, DIF ? 0 : 2, DIF>; \
+            cudaError_t e = cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
+            kc<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, pow_g, lg_m, lg_rows, scale); \
+            return cudaGetLastError(); }
+        switch (logLc) { B200_CONTIG_CASE(8) B200_CONTIG_CASE(9) B200_CONTIG_CASE(10) B200_CONTIG_CASE(11) B200_CONTIG_CASE(12) B200_CONTIG_CASE(13) default: break; }
+#undef B200_CONTIG_CASE
+    }
     auto kern = k_ntt_contig<DIF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const uint32_t grid = (uint32_t)((total_rows + rpc - 1) / rpc);
     kern<<<grid, 256, smem, s>>>(out, in, logLc, lg_e, rpc, rows_per_poly, (uint32_t)total_rows, in_stride, out_stride,
-                                 DIF ? T->tw_inv : T->tw_fwd, pow_g, lg_m, lg_rows, scale);
+                                 twt, pow_g, lg_m, lg_rows, scale);
     return cudaGetLastError();
 }
 

@@ -139,7 +139,7 @@ int main() {
 #define PERM(T, MB, BPS) { int nb = sms * BPS; float ms = time_ms([&] { k_perm<T, MB><<<nb, T>>>(d_out, pit, 7u); }); \
             double perms = (double)nb * T * pit; \
             printf("perm threads=%d minb=%d blocks/sm=%d  %8.3f ms  %8.3f Gperm/s  %8.2f Gmulmod/s-equiv\n", T, MB, BPS, ms, perms / ms * 1e-6, perms * 1356 / ms * 1e-6); }
-        PERM(128, 1, 4) PERM(128, 1, 8) PERM(128, 1, 12) PERM(256, 1, 2) PERM(256, 1, 4) PERM(256, 2, 4) PERM(256, 3, 6) PERM(512, 1, 2) PERM(64, 1, 16)
+        PERM(128, 1, 4) PERM(128, 1, 8) PERM(128, 1, 12) PERM(256, 1, 2) PERM(256, 1, 4) PERM(256, 2, 4) PERM(256, 3, 6) PERM(512, 1, 2) PERM(64, 1, 16) PERM(256, 4, 8) PERM(128, 8, 16) PERM(1024, 1, 1) PERM(384, 2, 4)
     }
     CK(cudaFree(d_out));
     return 0;
