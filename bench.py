@@ -84,10 +84,11 @@ class ClockSampler:
 def reference_arm(args):
     """The reference's CPU path, restated (oracle port; the risc0 crates are not buildable here -- DESIGN.md).
     Each step proves one bounded sample segment on all host threads; throughput is scaled to 2^20-row segments."""
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)      # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host thread
     from oracle import pyoracle as o
     o.lib()
     sample_po2 = 16
-    cores = os.cpu_count() or 1
     for i in range(args.warmup):
         o.prove(sample_po2 - 2, 0xB2000000 + i)
     t0 = time.perf_counter()
@@ -171,6 +172,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--slots", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="segments", choices=["segments", "tree"],
+                    help="segments: BASELINE configs 2/3 (default, the contract line); tree: config 4, prove+lift+join to one root")
+    ap.add_argument("--segments-per-gpu", type=int, default=4, help="tree mode: segments per rank")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -182,6 +186,9 @@ def main():
             reference_arm(args)
         return
 
+    # keep stdout clean for the single JSON line: NCCL / library banners go to stderr until the result is printed
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -203,6 +210,42 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.mode == "tree":
+        # BASELINE config 4: every rank proves + lifts its block, the Planner-shaped join DAG runs across ranks (NCCL
+        # send/recv of ~0.1 MB receipts), one root STARK lands on rank 0.
+        from boundless_b200 import VerifierContext
+        from boundless_b200.dist import prove_job
+        from boundless_b200.prover_server import KIND_LIFT, SuccinctReceipt
+        n_seg = args.segments_per_gpu * world
+        ctx = VerifierContext()
+        rec_words = srv.seal_words(srv._rec_circuit(KIND_LIFT))
+        def prove_and_lift(i):
+            return srv.lift(srv.prove_segment(ctx, Segment(index=i, po2=PO2)))
+        prove_job(min(world, 2) * 1, prove_and_lift, srv.join, lambda r: r.seal, lambda sl, c: SuccinctReceipt(sl, 2, c), rec_words,
+                  device=torch.device("cuda", local_rank))          # warm-up job
+        barrier()
+        t0 = time.perf_counter()
+        root, stats = prove_job(n_seg, prove_and_lift, srv.join, lambda r: r.seal, lambda sl, c: SuccinctReceipt(sl, 2, c), rec_words,
+                                device=torch.device("cuda", local_rank))
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt, float(stats["bytes_sent"])], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt[0:1], op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt[1:2], op=dist.ReduceOp.SUM)
+        if rank == 0:
+            out = {"metric": "job_segments_per_sec_to_root", "value": n_seg / float(tt[0]), "unit": "segments/s", "n_gpus": world,
+                   "steps": 1, "warmup": 1, "ms_per_step": float(tt[0]) * 1e3, "higher_is_better": True, "scaling": "weak",
+                   "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                   "config": {"workload": "config 4: %d x 1M-cycle segments -> prove + lift (po2 18) -> join tree -> one root" % n_seg,
+                              "segments": n_seg, "root_claim": list(root.claim), "nccl_bytes_moved": int(tt[1]),
+                              "joins": n_seg - 1, "timer": "wall clock sync-to-sync, max over ranks"}}
+            sys.stdout.flush(); os.dup2(real_stdout, 1); print(json.dumps(out), flush=True); os.dup2(2, 1)
+        srv.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     def run(n_steps, traces=None, first_index=0):
         """n_steps segments through the public API, `slots` in flight; returns (wall_s, device_ms)."""
@@ -289,6 +332,7 @@ def main():
             "roofline": roof, "roofline_int32": roof_int, "kernels": kernels,
         }
         if not args.no_cpu_baseline and world == 1:
+            os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
             from oracle import pyoracle as o          # checker / CPU baseline leg only
             o.lib()
             sample_po2 = 16
@@ -300,7 +344,10 @@ def main():
             out["cpu_baseline"] = {"value": 1.0 / (dt * scale), "unit": "segments/s", "cores": os.cpu_count(), "kind": "port",
                                    "sample": "one 2^%d-row segment (same widths/protocol) on all host threads, time scaled x%d" % (sample_po2, scale),
                                    "sample_seconds": dt, "verifies": o.verify(seal) == 0}
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     for _, _, p in pinned:
         L.b200_host_free(p)
     srv.close()

@@ -17,6 +17,7 @@ constexpr int GLOBALS = 16;
 // ---- per-device read-only tables (tables.cpp) --------------------------------------------------------
 struct DeviceTables {
     int device;
+    int sm_count;
     // stage twiddles, compact per-level layout: tw[2^(l-1) + i] = w_{2^l}^i, i < 2^(l-1), l <= 12
     uint32_t* tw_fwd;      // 4096 entries
     uint32_t* tw_inv;      // 4096 entries

@@ -309,6 +309,62 @@ __global__ void __launch_bounds__(512) k_ntt_strided_c(uint32_t* __restrict__ da
     }
 }
 
+// Persistent, double-buffered strided pass: 8-column tiles (32-byte sectors), LDGSTS (cp.async) stages the NEXT tile into
+// the second shared-memory buffer while the current one is transformed, so the HBM latency of a tile load is hidden
+// behind the butterflies of the previous tile instead of stalling the CTA.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int LOGL, bool DIF>
+__global__ void __launch_bounds__(256) k_ntt_strided_p(uint32_t* __restrict__ data, uint32_t row_stride, uint32_t tiles_per_poly,
+                                                       uint32_t num_tiles, size_t poly_stride, const uint32_t* __restrict__ tw_g,
+                                                       const uint32_t* __restrict__ pow_g, uint32_t lg_m) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    constexpr uint32_t L = 1u << LOGL, TILE = L * 8;
+    const uint32_t tid = threadIdx.x, nth = blockDim.x;
+    const uint32_t h = (lg_m + 1) / 2, lmask = (1u << h) - 1, mmask = (1u << lg_m) - 1;
+    const uint32_t* plo = pow_g; const uint32_t* phi = pow_g + (1u << h);
+    auto tile_ptr = [&](uint32_t tile) { return data + (size_t)(tile / tiles_per_poly) * poly_stride + (size_t)(tile % tiles_per_poly) * 8; };
+    auto issue_load = [&](uint32_t tile, uint32_t* buf) {
+        const uint32_t* g = tile_ptr(tile);
+        for (uint32_t ch = tid; ch < 2 * L; ch += nth) cp_async16(buf + (ch >> 1) * 8 + (ch & 1) * 4, g + (size_t)(ch >> 1) * row_stride + (ch & 1) * 4);
+        cp_async_commit();
+    };
+    uint32_t cur = 0;
+    uint32_t tile = blockIdx.x;
+    if (tile < num_tiles) issue_load(tile, smem);
+    for (; tile < num_tiles; tile += gridDim.x) {
+        uint32_t* buf = smem + cur * TILE;
+        const uint32_t next = tile + gridDim.x;
+        if (next < num_tiles) { issue_load(next, smem + (cur ^ 1) * TILE); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        NttStages<LOGL, 0, DIF>::run(buf, tw_g, tid, nth, 3, MkStrided{3});
+        uint32_t* g = data + (size_t)(tile / tiles_per_poly) * poly_stride + (size_t)(tile % tiles_per_poly) * 8;
+        const uint32_t col0 = (tile % tiles_per_poly) * 8;
+        for (uint32_t ch = tid; ch < 2 * L; ch += nth) {
+            const uint32_t r = ch >> 1, c4 = (ch & 1) * 4;
+            uint4 v = *reinterpret_cast<const uint4*>(buf + r * 8 + c4);
+            if (pow_g) {
+                const uint32_t d1 = bitrev(r, LOGL);
+                uint32_t e = ((col0 + c4) * d1) & mmask;
+                v.x = fp_mul(v.x, fp_mul(__ldg(plo + (e & lmask)), __ldg(phi + (e >> h)))); e = (e + d1) & mmask;
+                v.y = fp_mul(v.y, fp_mul(__ldg(plo + (e & lmask)), __ldg(phi + (e >> h)))); e = (e + d1) & mmask;
+                v.z = fp_mul(v.z, fp_mul(__ldg(plo + (e & lmask)), __ldg(phi + (e >> h)))); e = (e + d1) & mmask;
+                v.w = fp_mul(v.w, fp_mul(__ldg(plo + (e & lmask)), __ldg(phi + (e >> h))));
+            }
+            *reinterpret_cast<uint4*>(g + (size_t)r * row_stride + c4) = v;
+        }
+        __syncthreads();       // everyone done with buf before the next iteration's prefetch overwrites it
+        cur ^= 1;
+    }
+}
+
 // contiguous rows (rows_per_poly is a power of two: poly = R >> lg_rpp)
 template <int LOGLC, int LGE, bool DIF>
 __global__ void __launch_bounds__(256) k_ntt_contig_c(uint32_t* out, const uint32_t* in, uint32_t rows_per_cta, uint32_t lg_rpp,
@@ -414,6 +470,19 @@ static cudaError_t run_strided(const DeviceTables* T, uint32_t* d, uint32_t logL
     const uint32_t h = (lg_m + 1) / 2;
     size_t smem = ((size_t)(1u << logL) << lgTW) * 4 + ((size_t)4 << logL) + (pow_g ? ((size_t)4 << h) + ((size_t)4 << (lg_m - h)) : 0);
     const uint32_t* twt = DIF ? T->tw_inv : T->tw_fwd;
+    if (logL >= 6 && logL <= 11 && ncols % 8 == 0 && row_stride % 4 == 0 && poly_stride % 4 == 0 && ((uintptr_t)d & 15) == 0 &&
+        env_int("B200_NTT_PERSISTENT", 1)) {
+        // persistent double-buffered kernel: 2 x (L x 8 words) of shared memory per CTA
+        const size_t sm = (size_t)2 * ((size_t)8 << logL) * 4;
+        const uint32_t tpp = ncols / 8, num_tiles = tpp * count;
+        uint32_t per_sm = (uint32_t)(200 * 1024 / sm); if (per_sm > 4) per_sm = 4; if (per_sm < 1) per_sm = 1;
+        uint32_t grid = (uint32_t)T->sm_count * per_sm; if (grid > num_tiles) grid = num_tiles;
+#define B200_STRIDED_P_CASE(LL) case LL: { auto kp = k_ntt_strided_p<LL, DIF>; \
+            cudaError_t e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
+            kp<<<grid, 256, sm, s>>>(d, row_stride, tpp, num_tiles, poly_stride, twt, pow_g, lg_m); return cudaGetLastError(); }
+        switch (logL) { B200_STRIDED_P_CASE(6) B200_STRIDED_P_CASE(7) B200_STRIDED_P_CASE(8) B200_STRIDED_P_CASE(9) B200_STRIDED_P_CASE(10) B200_STRIDED_P_CASE(11) default: break; }
+#undef B200_STRIDED_P_CASE
+    }
     if (logL >= 6 && logL <= 11) {
         const size_t sm = ((size_t)(1u << logL) << lgTW) * 4;
 #define B200_STRIDED_CASE(LL) case LL: { auto kc = k_ntt_strided_c<LL, DIF>; \

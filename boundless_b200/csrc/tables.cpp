@@ -55,6 +55,7 @@ const DeviceTables* get_tables(int device) {
     DeviceTables* T = new DeviceTables();
     memset(T, 0, sizeof *T);
     T->device = device;
+    if (cudaDeviceGetAttribute(&T->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || T->sm_count <= 0) T->sm_count = 148;
     memcpy(T->rou_fwd, B200_ROU_FWD_MONT, sizeof T->rou_fwd);
     memcpy(T->rou_rev, B200_ROU_REV_MONT, sizeof T->rou_rev);
     bool ok = true;

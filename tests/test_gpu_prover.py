@@ -68,6 +68,28 @@ def test_lift_join_bit_exact(small_server, oracle):
     assert j.claim == (0, 1)
 
 
+def test_job_dag_with_real_proofs(small_server, oracle):
+    """BASELINE config 4 on one GPU: 3 segments -> prove + lift -> Planner-shaped joins -> root; every receipt on the
+    way is recomputed by the oracle (tasks/prove.rs:44-104 + tasks/join.rs:52-56 executed through dist.prove_job)."""
+    from boundless_b200 import Segment, VerifierContext
+    from boundless_b200.dist import prove_job
+    from boundless_b200.prover_server import KIND_JOIN, KIND_LIFT, RECURSION_WIDTHS, SuccinctReceipt
+    ctx = VerifierContext()
+    rp = small_server.opts.recursion_po2
+    root, stats = prove_job(3, lambda i: small_server.lift(small_server.prove_segment(ctx, Segment(index=i, po2=9))),
+                            small_server.join, lambda r: r.seal, lambda s, c: SuccinctReceipt(s, KIND_JOIN, c),
+                            small_server.seal_words(small_server._rec_circuit(KIND_LIFT)))
+    assert stats == {"proved": 3, "joined": 2, "sent": 0, "received": 0, "bytes_sent": 0}
+    assert root.claim == (0, 2)
+    def rec(kind, digest):
+        return oracle.prove(rp, int(digest[0]) | (int(digest[1]) << 32), *RECURSION_WIDTHS, kind=kind, input_digest=digest)
+    lifts = [rec(KIND_LIFT, oracle.seal_digest(oracle.prove(9, 0xB2000000 + i))) for i in range(3)]
+    j01 = rec(KIND_JOIN, oracle.hash_pair(oracle.seal_digest(lifts[0]), oracle.seal_digest(lifts[1])))
+    j012 = rec(KIND_JOIN, oracle.hash_pair(oracle.seal_digest(j01), oracle.seal_digest(lifts[2])))
+    assert np.array_equal(root.seal, j012)
+    assert oracle.verify(root.seal) == 0
+
+
 def test_two_slots_in_flight(small_server, oracle):
     from boundless_b200 import Segment
     a, b = Segment(index=100, po2=12), Segment(index=101, po2=13)
