@@ -133,8 +133,14 @@ def kernel_roofline(torch, L, pk):
     alg_bytes = rows * cols * 4 + rows * 32
     perms = rows * ((cols + 15) // 16)
     ach = alg_bytes / (ms * 1e-3) / 1e9
+    traffic = None
+    try:      # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
+            traffic = json.load(f)["k_p2_rows_2p22x208"]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roof = {"kernel": "k_p2_rows (K4, data group 2^22 x 208)", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-            "frac": ach / pk["hbm_gbs"], "traffic": None, "ms_per_launch": ms, "alg_bytes_per_launch": alg_bytes}
+            "frac": ach / pk["hbm_gbs"], "traffic": traffic, "ms_per_launch": ms, "alg_bytes_per_launch": alg_bytes}
     # the honest bound for this kernel is the INT32 pipe (SURVEY finding 8): report it beside the HBM figure
     gmul = perms * 1356 / (ms * 1e-3) / 1e9
     INT_PEAK = 3508.0   # Gmulmod/s, independent-chain Montgomery microbenchmark on this part (profiles/microbench_r01.txt)
@@ -170,7 +176,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--slots", type=int, default=2)
+    ap.add_argument("--slots", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="segments", choices=["segments", "tree"],
                     help="segments: BASELINE configs 2/3 (default, the contract line); tree: config 4, prove+lift+join to one root")

@@ -11,12 +11,14 @@
 // whole proof is enqueued without a host round trip (CUDA-graph friendly).
 #include "internal.h"
 #include "poseidon2.cuh"
+#include <cstdlib>
 
 namespace b200 {
 
 // K4 ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) k_p2_rows(uint32_t* __restrict__ out, const uint32_t* __restrict__ m, uint32_t rows,
-                                                    uint32_t cols, size_t col_stride) {
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_p2_rows(uint32_t* __restrict__ out, const uint32_t* __restrict__ m, uint32_t rows,
+                                                           uint32_t cols, size_t col_stride) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= rows) return;
     uint32_t st[24];
@@ -79,12 +81,19 @@ __global__ void __launch_bounds__(1024, 1) k_p2_fold_top(uint32_t* nodes, uint32
 cudaError_t launch_poseidon2_rows(uint32_t* d_out, const uint32_t* d_matrix, uint32_t rows, uint32_t cols, size_t col_stride,
                                   cudaStream_t s) {
     if (rows == 0) return cudaSuccess;
-    k_p2_rows<<<(rows + 255) / 256, 256, 0, s>>>(d_out, d_matrix, rows, cols, col_stride);
+    static const int cfg = getenv("B200_P2_CFG") ? atoi(getenv("B200_P2_CFG")) : 0;      // launch-shape A/B switch (tools/time_p2.py)
+    switch (cfg) {
+        case 1: B200_LAUNCH(k_p2_rows<256, 4>)<<<(rows + 255) / 256, 256, 0, s>>>(d_out, d_matrix, rows, cols, col_stride); break;
+        case 2: B200_LAUNCH(k_p2_rows<512, 2>)<<<(rows + 511) / 512, 512, 0, s>>>(d_out, d_matrix, rows, cols, col_stride); break;
+        case 3: B200_LAUNCH(k_p2_rows<1024, 1>)<<<(rows + 1023) / 1024, 1024, 0, s>>>(d_out, d_matrix, rows, cols, col_stride); break;
+        case 4: B200_LAUNCH(k_p2_rows<128, 4>)<<<(rows + 127) / 128, 128, 0, s>>>(d_out, d_matrix, rows, cols, col_stride); break;
+        default: B200_LAUNCH(k_p2_rows<256, 2>)<<<(rows + 255) / 256, 256, 0, s>>>(d_out, d_matrix, rows, cols, col_stride); break;
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_poseidon2_fold(uint32_t* d_out, const uint32_t* d_in, uint32_t n_out, cudaStream_t s) {
     if (n_out == 0) return cudaSuccess;
-    k_p2_fold<<<(n_out + 255) / 256, 256, 0, s>>>(d_out, d_in, n_out);
+    B200_LAUNCH(k_p2_fold)<<<(n_out + 255) / 256, 256, 0, s>>>(d_out, d_in, n_out);
     return cudaGetLastError();
 }
 cudaError_t launch_poseidon2_fold_tree(uint32_t* d_nodes, uint32_t lg_rows, cudaStream_t s) {
@@ -95,7 +104,7 @@ cudaError_t launch_poseidon2_fold_tree(uint32_t* d_nodes, uint32_t lg_rows, cuda
         if (e != cudaSuccess) return e;
         sz >>= 1;
     }
-    k_p2_fold_top<<<1, 1024, 0, s>>>(d_nodes, sz);
+    B200_LAUNCH(k_p2_fold_top)<<<1, 1024, 0, s>>>(d_nodes, sz);
     return cudaGetLastError();
 }
 
@@ -189,26 +198,26 @@ __global__ void k_set_globals(uint32_t* seal, uint32_t po2, uint32_t w_code, uin
 }
 cudaError_t launch_set_globals(uint32_t* d_seal, uint32_t po2, uint32_t w_code, uint32_t w_data, uint32_t w_accum, uint32_t kind,
                                uint64_t seed, int hash_seed, cudaStream_t s) {
-    k_set_globals<<<1, 1, 0, s>>>(d_seal, po2, w_code, w_data, w_accum, kind, seed, hash_seed);
+    B200_LAUNCH(k_set_globals)<<<1, 1, 0, s>>>(d_seal, po2, w_code, w_data, w_accum, kind, seed, hash_seed);
     return cudaGetLastError();
 }
 
-cudaError_t launch_iop_init(Transcript* t, cudaStream_t s) { k_iop_init<<<1, 1, 0, s>>>(t); return cudaGetLastError(); }
-cudaError_t launch_iop_commit(Transcript* t, const uint32_t* d, cudaStream_t s) { k_iop_commit<<<1, 1, 0, s>>>(t, d); return cudaGetLastError(); }
+cudaError_t launch_iop_init(Transcript* t, cudaStream_t s) { B200_LAUNCH(k_iop_init)<<<1, 1, 0, s>>>(t); return cudaGetLastError(); }
+cudaError_t launch_iop_commit(Transcript* t, const uint32_t* d, cudaStream_t s) { B200_LAUNCH(k_iop_commit)<<<1, 1, 0, s>>>(t, d); return cudaGetLastError(); }
 cudaError_t launch_iop_commit_elems(Transcript* t, const uint32_t* e, uint32_t count, uint32_t* dout, cudaStream_t s) {
-    k_iop_commit_elems<<<1, 1, 0, s>>>(t, e, count, dout); return cudaGetLastError();
+    B200_LAUNCH(k_iop_commit_elems)<<<1, 1, 0, s>>>(t, e, count, dout); return cudaGetLastError();
 }
 cudaError_t launch_iop_draw_ext(Transcript* t, uint32_t* out, uint32_t n_ext, cudaStream_t s) {
-    k_iop_draw<<<1, 1, 0, s>>>(t, out, n_ext * 4, 0); return cudaGetLastError();
+    B200_LAUNCH(k_iop_draw)<<<1, 1, 0, s>>>(t, out, n_ext * 4, 0); return cudaGetLastError();
 }
 cudaError_t launch_iop_draw_bits(Transcript* t, uint32_t* out, uint32_t n, uint32_t bits, cudaStream_t s) {
-    k_iop_draw<<<1, 1, 0, s>>>(t, out, n, bits); return cudaGetLastError();
+    B200_LAUNCH(k_iop_draw)<<<1, 1, 0, s>>>(t, out, n, bits); return cudaGetLastError();
 }
 cudaError_t launch_hash_elems(uint32_t* dout, const uint32_t* e, uint32_t count, cudaStream_t s) {
-    k_hash_elems<<<1, 1, 0, s>>>(dout, e, count); return cudaGetLastError();
+    B200_LAUNCH(k_hash_elems)<<<1, 1, 0, s>>>(dout, e, count); return cudaGetLastError();
 }
 cudaError_t launch_hash_pair_one(uint32_t* out, const uint32_t* a, const uint32_t* b, cudaStream_t s) {
-    k_hash_pair_one<<<1, 1, 0, s>>>(out, a, b); return cudaGetLastError();
+    B200_LAUNCH(k_hash_pair_one)<<<1, 1, 0, s>>>(out, a, b); return cudaGetLastError();
 }
 
 }  // namespace b200

@@ -3,8 +3,15 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <cuda_runtime.h>
+#include <atomic>
 
 namespace b200 {
+
+// every kernel launch of the library goes through B200_LAUNCH so that b200_kernel_launches() reports real launches
+extern std::atomic<uint64_t> g_kernel_launches;
+template <typename F>
+inline F* count_launch(F* f) { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); return f; }
+#define B200_LAUNCH(...) ::b200::count_launch(__VA_ARGS__)
 
 constexpr int MAX_LG = 24;          // largest transform size 2^24
 constexpr int QUERIES = 50;

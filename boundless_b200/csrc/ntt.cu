@@ -479,7 +479,7 @@ static cudaError_t run_strided(const DeviceTables* T, uint32_t* d, uint32_t logL
         uint32_t grid = (uint32_t)T->sm_count * per_sm; if (grid > num_tiles) grid = num_tiles;
 #define B200_STRIDED_P_CASE(LL) case LL: { auto kp = k_ntt_strided_p<LL, DIF>; \
             cudaError_t e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
-            kp<<<grid, 256, sm, s>>>(d, row_stride, tpp, num_tiles, poly_stride, twt, pow_g, lg_m); return cudaGetLastError(); }
+            B200_LAUNCH(kp)<<<grid, 256, sm, s>>>(d, row_stride, tpp, num_tiles, poly_stride, twt, pow_g, lg_m); return cudaGetLastError(); }
         switch (logL) { B200_STRIDED_P_CASE(6) B200_STRIDED_P_CASE(7) B200_STRIDED_P_CASE(8) B200_STRIDED_P_CASE(9) B200_STRIDED_P_CASE(10) B200_STRIDED_P_CASE(11) default: break; }
 #undef B200_STRIDED_P_CASE
     }
@@ -487,14 +487,14 @@ static cudaError_t run_strided(const DeviceTables* T, uint32_t* d, uint32_t logL
         const size_t sm = ((size_t)(1u << logL) << lgTW) * 4;
 #define B200_STRIDED_CASE(LL) case LL: { auto kc = k_ntt_strided_c<LL, DIF>; \
             cudaError_t e = cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
-            kc<<<tiles_per_poly * count, env_int("B200_NTT_THREADS", 256), sm, s>>>(d, lgTW, row_stride, tiles_per_poly, poly_stride, twt, pow_g, lg_m); return cudaGetLastError(); }
+            B200_LAUNCH(kc)<<<tiles_per_poly * count, env_int("B200_NTT_THREADS", 256), sm, s>>>(d, lgTW, row_stride, tiles_per_poly, poly_stride, twt, pow_g, lg_m); return cudaGetLastError(); }
         switch (logL) { B200_STRIDED_CASE(6) B200_STRIDED_CASE(7) B200_STRIDED_CASE(8) B200_STRIDED_CASE(9) B200_STRIDED_CASE(10) B200_STRIDED_CASE(11) default: break; }
 #undef B200_STRIDED_CASE
     }
     auto kern = k_ntt_strided<DIF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<tiles_per_poly * count, 512, smem, s>>>(d, logL, lgTW, row_stride, tiles_per_poly, poly_stride, twt, pow_g, lg_m);
+    B200_LAUNCH(kern)<<<tiles_per_poly * count, 512, smem, s>>>(d, logL, lgTW, row_stride, tiles_per_poly, poly_stride, twt, pow_g, lg_m);
     return cudaGetLastError();
 }
 
@@ -515,7 +515,7 @@ static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32
         const size_t sm = (size_t)rpc * (Lc + (Lc >> 4)) * 4;
 #define B200_CONTIG_CASE(LL) case LL: { auto kc = k_ntt_contig_c<LL, DIF ? 0 : 2, DIF>; \
             cudaError_t e = cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
-            kc<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, pow_g, lg_m, lg_rows, scale); \
+            B200_LAUNCH(kc)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, pow_g, lg_m, lg_rows, scale); \
             return cudaGetLastError(); }
         switch (logLc) { B200_CONTIG_CASE(8) B200_CONTIG_CASE(9) B200_CONTIG_CASE(10) B200_CONTIG_CASE(11) B200_CONTIG_CASE(12) B200_CONTIG_CASE(13) default: break; }
 #undef B200_CONTIG_CASE
@@ -523,7 +523,7 @@ static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32
     auto kern = k_ntt_contig<DIF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, 256, smem, s>>>(out, in, logLc, lg_e, rpc, rows_per_poly, (uint32_t)total_rows, in_stride, out_stride,
+    B200_LAUNCH(kern)<<<grid, 256, smem, s>>>(out, in, logLc, lg_e, rpc, rows_per_poly, (uint32_t)total_rows, in_stride, out_stride,
                                  twt, pow_g, lg_m, lg_rows, scale);
     return cudaGetLastError();
 }
@@ -567,14 +567,14 @@ cudaError_t launch_batch_ntt(const DeviceTables* T, uint32_t* d_io, uint32_t lg_
 cudaError_t launch_zk_shift(const DeviceTables* T, uint32_t* d_io, uint32_t lg_n, uint32_t count, cudaStream_t s) {
     const size_t total = (size_t)count << lg_n;
     if (total == 0) return cudaSuccess;
-    k_zk_shift<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_io, lg_n, total, T->p3lo, T->p3hi);
+    B200_LAUNCH(k_zk_shift)<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_io, lg_n, total, T->p3lo, T->p3hi);
     return cudaGetLastError();
 }
 
 cudaError_t launch_bit_reverse(uint32_t* d_io, uint32_t lg_n, uint32_t count, cudaStream_t s) {
     const size_t total = (size_t)count << lg_n;
     if (total == 0) return cudaSuccess;
-    k_bit_reverse<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_io, lg_n, total);
+    B200_LAUNCH(k_bit_reverse)<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_io, lg_n, total);
     return cudaGetLastError();
 }
 

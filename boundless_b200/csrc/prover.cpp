@@ -71,7 +71,7 @@ struct SealLayout {
     }
 };
 
-static std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_kernel_launches{0};
 
 // bump allocator over one cudaMalloc'd arena
 struct Arena {
@@ -151,7 +151,7 @@ static const char* slot_init(b200_prover* p, Slot& s) {
     return nullptr;
 }
 
-#define KL(x) do { cudaError_t e__ = (x); g_launches.fetch_add(1, std::memory_order_relaxed); if (e__ != cudaSuccess) { set_error("b200: %s: %s", #x, cudaGetErrorString(e__)); return last_error(); } } while (0)
+#define KL(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { set_error("b200: %s: %s", #x, cudaGetErrorString(e__)); return last_error(); } } while (0)
 
 // iNTT + zk_shift (optional) + expand/NTT + leaf hash + tree + top layer to the seal + rng.mix(root)
 static const char* commit_group(b200_prover* p, Slot& s, uint32_t* coeffs, uint32_t* evals, uint32_t* nodes, uint32_t po2,
@@ -279,7 +279,7 @@ static const char* seal_digest_async(b200_prover* p, Slot& s, const uint32_t* h_
 
 extern "C" {
 
-uint64_t b200_kernel_launches(void) { return g_launches.load(); }
+uint64_t b200_kernel_launches(void) { return g_kernel_launches.load(); }
 
 size_t b200_seal_words(const b200_circuit* c) {
     if (check_circuit(c)) return 0;

@@ -33,7 +33,7 @@ __global__ void k_gen_trace(uint32_t* __restrict__ out, uint64_t seed, uint64_t 
 }
 cudaError_t launch_gen_trace(uint32_t* d_out, uint64_t seed, const uint32_t* d_seed_words, uint64_t count, cudaStream_t s) {
     if (!count) return cudaSuccess;
-    k_gen_trace<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_out, seed, count, d_seed_words);
+    B200_LAUNCH(k_gen_trace)<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_out, seed, count, d_seed_words);
     return cudaGetLastError();
 }
 
@@ -52,7 +52,7 @@ __global__ void k_accumulate(uint32_t* __restrict__ io, uint32_t rows, uint32_t 
     }
 }
 cudaError_t launch_accumulate(uint32_t* d_acc_io, uint32_t rows, uint32_t w_accum, const uint32_t* d_mix, cudaStream_t s) {
-    k_accumulate<<<(rows + 255) / 256, 256, 0, s>>>(d_acc_io, rows, w_accum, d_mix);
+    B200_LAUNCH(k_accumulate)<<<(rows + 255) / 256, 256, 0, s>>>(d_acc_io, rows, w_accum, d_mix);
     return cudaGetLastError();
 }
 
@@ -64,7 +64,7 @@ __global__ void k_powers(uint32_t* __restrict__ out, const uint32_t* __restrict_
 }
 cudaError_t launch_powers(uint32_t* d_out, const uint32_t* d_base, uint32_t count, cudaStream_t s) {
     if (!count) return cudaSuccess;
-    k_powers<<<(count + 127) / 128, 128, 0, s>>>(d_out, d_base, count);
+    B200_LAUNCH(k_powers)<<<(count + 127) / 128, 128, 0, s>>>(d_out, d_base, count);
     return cudaGetLastError();
 }
 
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) k_eval_check(uint32_t* __restrict__ plane
 cudaError_t launch_eval_check(uint32_t* d_planes, const uint32_t* d_evals, uint32_t lg_domain, uint32_t w_code, uint32_t w_data,
                               uint32_t w_accum, const uint32_t* d_pmix, cudaStream_t s) {
     const uint32_t D = 1u << lg_domain, nterms = (w_code + w_data + w_accum) / 4 + w_accum;
-    k_eval_check<<<(D + 255) / 256, 256, nterms * 16, s>>>(d_planes, d_evals, D, w_code, w_data, w_accum, d_pmix);
+    B200_LAUNCH(k_eval_check)<<<(D + 255) / 256, 256, nterms * 16, s>>>(d_planes, d_evals, D, w_code, w_data, w_accum, d_pmix);
     return cudaGetLastError();
 }
 
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) k_fri_fold(uint32_t* __restrict__ out, co
 cudaError_t launch_fri_fold(uint32_t* d_out, const uint32_t* d_in, uint32_t in_size, const uint32_t* d_mix, cudaStream_t s) {
     const uint32_t cnt = in_size / FRI_FOLD;
     if (!cnt) return cudaSuccess;
-    k_fri_fold<<<(cnt + 255) / 256, 256, 0, s>>>(d_out, d_in, in_size, d_mix);
+    B200_LAUNCH(k_fri_fold)<<<(cnt + 255) / 256, 256, 0, s>>>(d_out, d_in, in_size, d_mix);
     return cudaGetLastError();
 }
 
@@ -204,12 +204,12 @@ cudaError_t launch_evaluate(uint32_t* d_out_a, uint32_t* d_out_b, const uint32_t
     uint32_t* plo_b = phi_a + 4 * (size_t)NCH; uint32_t* phi_b = plo_b + 4 * (size_t)CH;
     uint32_t* part_a = phi_b + 4 * (size_t)NCH; uint32_t* part_b = part_a + 4 * (size_t)count * NCH;
     const uint32_t tn = CH > NCH ? CH : NCH;
-    k_ev_tables<<<(tn + 127) / 128, 128, 0, s>>>(plo_a, phi_a, d_x, lg_n, lc);
-    if (d_xb) k_ev_tables<<<(tn + 127) / 128, 128, 0, s>>>(plo_b, phi_b, d_xb, lg_n, lc);
+    B200_LAUNCH(k_ev_tables)<<<(tn + 127) / 128, 128, 0, s>>>(plo_a, phi_a, d_x, lg_n, lc);
+    if (d_xb) B200_LAUNCH(k_ev_tables)<<<(tn + 127) / 128, 128, 0, s>>>(plo_b, phi_b, d_xb, lg_n, lc);
     dim3 grid(NCH, count);
-    k_ev_partial<<<grid, 256, 0, s>>>(part_a, part_b, d_coeffs, lg_n, lc, plo_a, d_xb ? plo_b : nullptr, b0, b1);
-    k_ev_reduce<<<count, 128, 0, s>>>(d_out_a, part_a, phi_a, NCH);
-    if (d_xb && b1 > b0) k_ev_reduce<<<b1 - b0, 128, 0, s>>>(d_out_b, part_b, phi_b, NCH);
+    B200_LAUNCH(k_ev_partial)<<<grid, 256, 0, s>>>(part_a, part_b, d_coeffs, lg_n, lc, plo_a, d_xb ? plo_b : nullptr, b0, b1);
+    B200_LAUNCH(k_ev_reduce)<<<count, 128, 0, s>>>(d_out_a, part_a, phi_a, NCH);
+    if (d_xb && b1 > b0) B200_LAUNCH(k_ev_reduce)<<<b1 - b0, 128, 0, s>>>(d_out_b, part_b, phi_b, NCH);
     return cudaGetLastError();
 }
 
@@ -221,7 +221,7 @@ __global__ void k_deep_points(uint32_t* pts, const uint32_t* z, uint32_t rou_rev
     st_fp4(pts + 8, fp4_mul(z2, z2));
 }
 cudaError_t launch_deep_points(uint32_t* d_pts, const uint32_t* d_z, uint32_t rou_rev_n, cudaStream_t s) {
-    k_deep_points<<<1, 1, 0, s>>>(d_pts, d_z, rou_rev_n);
+    B200_LAUNCH(k_deep_points)<<<1, 1, 0, s>>>(d_pts, d_z, rou_rev_n);
     return cudaGetLastError();
 }
 
@@ -359,11 +359,11 @@ __global__ void __launch_bounds__(DV_T) k_deep_divide(uint32_t* __restrict__ pla
 cudaError_t launch_deep(const DeepArgs& a, cudaStream_t s) {
     const uint32_t N = 1u << a.lg_n, T = a.W + a.w_accum + CHECK_COLS;
     const uint32_t nchunks = (N + DV_CH - 1) / DV_CH;
-    k_deep_mix<<<(N + 255) / 256, 256, T * 16, s>>>(a.combos, a.coeffs, a.check_coeffs, a.u, a.mix_pows, a.lg_n, a.W, a.w_accum);
+    B200_LAUNCH(k_deep_mix)<<<(N + 255) / 256, 256, T * 16, s>>>(a.combos, a.coeffs, a.check_coeffs, a.u, a.mix_pows, a.lg_n, a.W, a.w_accum);
     dim3 g2(nchunks, 3);
-    k_deep_chunk_vals<<<g2, DV_T, 0, s>>>(a.chunk_vals, a.combos, a.pts, N, nchunks);
-    k_deep_chunk_scan<<<3, 1, 0, s>>>(a.chunk_carry, a.chunk_vals, a.pts, nchunks);
-    k_deep_divide<<<nchunks, DV_T, 0, s>>>(a.f_planes, a.combos, a.chunk_carry, a.pts, a.lg_n, nchunks);
+    B200_LAUNCH(k_deep_chunk_vals)<<<g2, DV_T, 0, s>>>(a.chunk_vals, a.combos, a.pts, N, nchunks);
+    B200_LAUNCH(k_deep_chunk_scan)<<<3, 1, 0, s>>>(a.chunk_carry, a.chunk_vals, a.pts, nchunks);
+    B200_LAUNCH(k_deep_divide)<<<nchunks, DV_T, 0, s>>>(a.f_planes, a.combos, a.chunk_carry, a.pts, a.lg_n, nchunks);
     return cudaGetLastError();
 }
 
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(128) k_gather(uint32_t* __restrict__ seal, uin
 cudaError_t launch_gather_queries(uint32_t* d_seal, uint32_t query_base, uint32_t query_words, const uint32_t* d_pos,
                                   const GatherTree* d_trees, uint32_t n_trees, cudaStream_t s) {
     dim3 grid(n_trees, QUERIES);
-    k_gather<<<grid, 128, 0, s>>>(d_seal, query_base, query_words, d_pos, d_trees);
+    B200_LAUNCH(k_gather)<<<grid, 128, 0, s>>>(d_seal, query_base, query_words, d_pos, d_trees);
     return cudaGetLastError();
 }
 

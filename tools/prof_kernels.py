@@ -28,6 +28,13 @@ if "rows" in what:
     for _ in range(2):
         assert L.b200_poseidon2_rows(p(d), p(m), rows, cols, None) is None
     torch.cuda.synchronize()
+if "rows208" in what:      # the bench's roofline kernel: K4 on the data group (2^22 x 208)
+    rows, cols = 1 << 22, 208
+    m = torch.randint(0, P, (rows * cols,), dtype=torch.int32, device="cuda")
+    d = torch.empty(rows * 8, dtype=torch.int32, device="cuda")
+    for _ in range(2):
+        assert L.b200_poseidon2_rows(p(d), p(m), rows, cols, None) is None
+    torch.cuda.synchronize()
 if "fold" in what:
     nodes = torch.randint(0, P, (2 * (1 << 22) * 8,), dtype=torch.int32, device="cuda")
     assert L.b200_poseidon2_fold(p(nodes), p(nodes[(1 << 22) * 8:]), 1 << 21, None) is None
