@@ -262,6 +262,14 @@ struct NttStages {
     }
 };
 
+struct AddrStridedPad8 {   // 8-column tile, one padding row per 16 rows: groups of a warp that sit 16 rows apart hit different banks
+    uint32_t t;
+    __device__ __forceinline__ uint32_t operator()(uint32_t pos) const { return ((pos + (pos >> 4)) << 3) + t; }
+};
+struct MkStridedPad8 {
+    __device__ __forceinline__ uint32_t gidx(uint32_t w) const { return w >> 3; }
+    __device__ __forceinline__ AddrStridedPad8 addr(uint32_t w) const { return AddrStridedPad8{w & 7u}; }
+};
 struct MkStrided {      // work item w -> (group index, column t)
     uint32_t lgTW;
     __device__ __forceinline__ uint32_t gidx(uint32_t w) const { return w >> lgTW; }
@@ -321,18 +329,18 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int LOGL, bool DIF>
-__global__ void __launch_bounds__(256) k_ntt_strided_p(uint32_t* __restrict__ data, uint32_t row_stride, uint32_t tiles_per_poly,
+__global__ void __launch_bounds__(512) k_ntt_strided_p(uint32_t* __restrict__ data, uint32_t row_stride, uint32_t tiles_per_poly,
                                                        uint32_t num_tiles, size_t poly_stride, const uint32_t* __restrict__ tw_g,
                                                        const uint32_t* __restrict__ pow_g, uint32_t lg_m) {
     extern __shared__ __align__(16) uint32_t smem[];
-    constexpr uint32_t L = 1u << LOGL, TILE = L * 8;
+    constexpr uint32_t L = 1u << LOGL, TILE = (L + (L >> 4)) * 8;
     const uint32_t tid = threadIdx.x, nth = blockDim.x;
     const uint32_t h = (lg_m + 1) / 2, lmask = (1u << h) - 1, mmask = (1u << lg_m) - 1;
     const uint32_t* plo = pow_g; const uint32_t* phi = pow_g + (1u << h);
     auto tile_ptr = [&](uint32_t tile) { return data + (size_t)(tile / tiles_per_poly) * poly_stride + (size_t)(tile % tiles_per_poly) * 8; };
     auto issue_load = [&](uint32_t tile, uint32_t* buf) {
         const uint32_t* g = tile_ptr(tile);
-        for (uint32_t ch = tid; ch < 2 * L; ch += nth) cp_async16(buf + (ch >> 1) * 8 + (ch & 1) * 4, g + (size_t)(ch >> 1) * row_stride + (ch & 1) * 4);
+        for (uint32_t ch = tid; ch < 2 * L; ch += nth) { const uint32_t r = ch >> 1; cp_async16(buf + (r + (r >> 4)) * 8 + (ch & 1) * 4, g + (size_t)r * row_stride + (ch & 1) * 4); }
         cp_async_commit();
     };
     uint32_t cur = 0;
@@ -344,12 +352,12 @@ __global__ void __launch_bounds__(256) k_ntt_strided_p(uint32_t* __restrict__ da
         if (next < num_tiles) { issue_load(next, smem + (cur ^ 1) * TILE); cp_async_wait<1>(); }
         else cp_async_wait<0>();
         __syncthreads();
-        NttStages<LOGL, 0, DIF>::run(buf, tw_g, tid, nth, 3, MkStrided{3});
+        NttStages<LOGL, 0, DIF>::run(buf, tw_g, tid, nth, 3, MkStridedPad8{});
         uint32_t* g = data + (size_t)(tile / tiles_per_poly) * poly_stride + (size_t)(tile % tiles_per_poly) * 8;
         const uint32_t col0 = (tile % tiles_per_poly) * 8;
         for (uint32_t ch = tid; ch < 2 * L; ch += nth) {
             const uint32_t r = ch >> 1, c4 = (ch & 1) * 4;
-            uint4 v = *reinterpret_cast<const uint4*>(buf + r * 8 + c4);
+            uint4 v = *reinterpret_cast<const uint4*>(buf + (r + (r >> 4)) * 8 + c4);
             if (pow_g) {
                 const uint32_t d1 = bitrev(r, LOGL);
                 uint32_t e = ((col0 + c4) * d1) & mmask;
@@ -473,13 +481,13 @@ static cudaError_t run_strided(const DeviceTables* T, uint32_t* d, uint32_t logL
     if (logL >= 6 && logL <= 11 && ncols % 8 == 0 && row_stride % 4 == 0 && poly_stride % 4 == 0 && ((uintptr_t)d & 15) == 0 &&
         env_int("B200_NTT_PERSISTENT", 1)) {
         // persistent double-buffered kernel: 2 x (L x 8 words) of shared memory per CTA
-        const size_t sm = (size_t)2 * ((size_t)8 << logL) * 4;
+        const size_t sm = (size_t)2 * (((size_t)8 << logL) + ((size_t)8 << logL) / 16) * 4;
         const uint32_t tpp = ncols / 8, num_tiles = tpp * count;
-        uint32_t per_sm = (uint32_t)(200 * 1024 / sm); if (per_sm > 4) per_sm = 4; if (per_sm < 1) per_sm = 1;
+        uint32_t per_sm = (uint32_t)(226 * 1024 / (sm + 1024)); if (per_sm > 4) per_sm = 4; if (per_sm < 1) per_sm = 1;
         uint32_t grid = (uint32_t)T->sm_count * per_sm; if (grid > num_tiles) grid = num_tiles;
 #define B200_STRIDED_P_CASE(LL) case LL: { auto kp = k_ntt_strided_p<LL, DIF>; \
             cudaError_t e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
-            B200_LAUNCH(kp)<<<grid, 256, sm, s>>>(d, row_stride, tpp, num_tiles, poly_stride, twt, pow_g, lg_m); return cudaGetLastError(); }
+            B200_LAUNCH(kp)<<<grid, env_int("B200_NTT_THREADS", 512), sm, s>>>(d, row_stride, tpp, num_tiles, poly_stride, twt, pow_g, lg_m); return cudaGetLastError(); }
         switch (logL) { B200_STRIDED_P_CASE(6) B200_STRIDED_P_CASE(7) B200_STRIDED_P_CASE(8) B200_STRIDED_P_CASE(9) B200_STRIDED_P_CASE(10) B200_STRIDED_P_CASE(11) default: break; }
 #undef B200_STRIDED_P_CASE
     }

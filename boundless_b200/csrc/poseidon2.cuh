@@ -92,4 +92,35 @@ __device__ __forceinline__ void p2_permute(uint32_t (&c)[24]) {
     }
 }
 
+// Two independent states per thread, software-pipelined by half a round: while state A is in its (ALU-heavy) linear
+// layer, state B is in its (multiplier-heavy) S-box layer, so both integer pipes stay busy inside one warp.
+__device__ __forceinline__ void p2_sbox_full(uint32_t (&c)[24], int rc_base) {
+#pragma unroll
+    for (int i = 0; i < 24; i++) c[i] = p2_sbox(fp_add(c[i], c_rc[rc_base + i]));
+}
+__device__ __forceinline__ void p2_permute2(uint32_t (&a)[24], uint32_t (&b)[24]) {
+    p2_m_ext(a); p2_m_ext(b);
+    p2_sbox_full(a, 0);
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+        p2_m_ext(a); p2_sbox_full(b, 24 * r);
+        if (r < 3) p2_sbox_full(a, 24 * (r + 1));
+        p2_m_ext(b);
+    }
+    a[0] = p2_sbox(fp_add(a[0], c_rc[96]));
+#pragma unroll 1
+    for (int r = 0; r < 21; r++) {
+        p2_m_int(a); b[0] = p2_sbox(fp_add(b[0], c_rc[96 + r]));
+        if (r < 20) a[0] = p2_sbox(fp_add(a[0], c_rc[97 + r]));
+        p2_m_int(b);
+    }
+    p2_sbox_full(a, 117);
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+        p2_m_ext(a); p2_sbox_full(b, 117 + 24 * r);
+        if (r < 3) p2_sbox_full(a, 117 + 24 * (r + 1));
+        p2_m_ext(b);
+    }
+}
+
 }  // namespace b200

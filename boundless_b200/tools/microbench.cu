@@ -87,6 +87,24 @@ __global__ void __launch_bounds__(THREADS, MINB) k_perm(uint32_t* out, int iters
     out[blockIdx.x * THREADS + threadIdx.x] = s;
 }
 
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_perm2(uint32_t* out, int iters, uint32_t seed) {
+    uint32_t sa[24], sb[24];
+#pragma unroll
+    for (int i = 0; i < 24; i++) { sa[i] = (uint32_t)(((uint64_t)(blockIdx.x * THREADS + threadIdx.x) * 48u + i + seed) % P); sb[i] = (sa[i] + 24u) % P; }
+    for (int it = 0; it < iters; it++) p2_permute2(sa, sb);
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 24; i++) s ^= sa[i] ^ sb[i];
+    out[blockIdx.x * THREADS + threadIdx.x] = s;
+}
+__global__ void k_kat2(uint32_t* out) {
+    uint32_t a[24], b[24];
+    for (int i = 0; i < 24; i++) { a[i] = fp_to_mont(i); b[i] = fp_to_mont(i); }
+    p2_permute2(a, b);
+    for (int i = 0; i < 24; i++) { out[i] = fp_from_mont(a[i]); out[24 + i] = fp_from_mont(b[i]); }
+}
+
 __global__ void k_kat(uint32_t* out) {
     uint32_t st[24];
     for (int i = 0; i < 24; i++) st[i] = fp_to_mont(i);
@@ -121,6 +139,10 @@ int main() {
     uint32_t h[24]; CK(cudaMemcpy(h, d_out, 96, cudaMemcpyDeviceToHost));
     int ok = 1; for (int i = 0; i < 24; i++) ok &= (h[i] == KAT[i]);
     printf("poseidon2_kat %s\n", ok ? "PASS" : "FAIL");
+    k_kat2<<<1, 1>>>(d_out); CK(cudaDeviceSynchronize());
+    uint32_t h2[48]; CK(cudaMemcpy(h2, d_out, 192, cudaMemcpyDeviceToHost));
+    int ok2 = 1; for (int i = 0; i < 24; i++) ok2 &= (h2[i] == KAT[i]) && (h2[24 + i] == KAT[i]);
+    printf("poseidon2_kat2 (two interleaved states) %s\n", ok2 ? "PASS" : "FAIL");
 
     const char* names[] = {"imad_lo_rrr", "imad_hi_rr", "imad_wide", "iadd", "viaddmin_u32", "imad_lo_imm", "imad_hi_imm", "lop3", "shf"};
     int blocks = sms * 8, iters = 2000;
@@ -140,6 +162,13 @@ int main() {
             double perms = (double)nb * T * pit; \
             printf("perm threads=%d minb=%d blocks/sm=%d  %8.3f ms  %8.3f Gperm/s  %8.2f Gmulmod/s-equiv\n", T, MB, BPS, ms, perms / ms * 1e-6, perms * 1356 / ms * 1e-6); }
         PERM(128, 1, 4) PERM(128, 1, 8) PERM(128, 1, 12) PERM(256, 1, 2) PERM(256, 1, 4) PERM(256, 2, 4) PERM(256, 3, 6) PERM(512, 1, 2) PERM(64, 1, 16) PERM(256, 4, 8) PERM(128, 8, 16) PERM(1024, 1, 1) PERM(384, 2, 4)
+    }
+    {
+        int pit = 64;
+#define PERM2(T, MB, BPS) { int nb = sms * BPS; float ms = time_ms([&] { k_perm2<T, MB><<<nb, T>>>(d_out, pit, 7u); }); \
+            double perms = 2.0 * nb * T * pit; \
+            printf("perm2 threads=%d minb=%d blocks/sm=%d  %8.3f ms  %8.3f Gperm/s\n", T, MB, BPS, ms, perms / ms * 1e-6); }
+        PERM2(128, 1, 4) PERM2(128, 2, 8) PERM2(256, 1, 2) PERM2(256, 2, 4) PERM2(512, 1, 2) PERM2(64, 4, 16) PERM2(128, 4, 8)
     }
     CK(cudaFree(d_out));
     return 0;
