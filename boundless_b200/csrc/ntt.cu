@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) k_ntt_contig(uint32_t* __restrict__ out, 
 // Specialised (compile-time size) passes: all stage strides, twiddle offsets and loop counts are immediates,
 // tables are read through the read-only path (L1-resident, no per-CTA staging), so a CTA only stages its data tile.
 // =========================================================================================================
-template <int K, int LB, bool DIF, typename ADDR>
+template <int K, int LB, bool DIF, bool TWS = false, typename ADDR>
 __device__ __forceinline__ void ntt_stage_c(uint32_t* s, const uint32_t* __restrict__ tw, uint32_t gidx, ADDR addr) {
     constexpr int R = 1 << K;
     constexpr uint32_t q = (1u << LB) >> K;
@@ -227,7 +227,8 @@ __device__ __forceinline__ void ntt_stage_c(uint32_t* s, const uint32_t* __restr
 #pragma unroll
         for (int j = 0; j < R; j++) {
             if ((j & half) == 0) {
-                const uint32_t w = __ldg(twp + ((1u << LB) >> (l + 1)) + (j & (half - 1)) * q);
+                const uint32_t* wp = twp + ((1u << LB) >> (l + 1)) + (j & (half - 1)) * q;
+                const uint32_t w = TWS ? *wp : __ldg(wp);      // TWS: table staged in shared memory by TMA
                 const uint32_t a = x[j], bb = x[j + half];
                 if (DIF) {
                     x[j] = fp_add(a, bb);
@@ -245,7 +246,7 @@ __device__ __forceinline__ void ntt_stage_c(uint32_t* s, const uint32_t* __restr
 }
 
 // runs all stages of a length-2^LOGL transform held in shared memory; LOW = number of already-done low levels (DIT expand)
-template <int LOGL, int LOW, bool DIF, int DONE = 0>
+template <int LOGL, int LOW, bool DIF, int DONE = 0, bool TWS = false>
 struct NttStages {
     template <typename MK>
     static __device__ __forceinline__ void run(uint32_t* s, const uint32_t* tw, uint32_t tid, uint32_t nth, uint32_t nbatch_shift, MK mk) {
@@ -255,9 +256,9 @@ struct NttStages {
             constexpr int K = DIF ? (REM >= 4 ? 4 : REM) : ((REM % 4) ? (REM % 4) : 4);
             constexpr int LB = DIF ? (LOGL - DONE) : (LOW + DONE + K);
             const uint32_t total = ((1u << LOGL) >> K) << nbatch_shift;
-            for (uint32_t w = tid; w < total; w += nth) ntt_stage_c<K, LB, DIF>(s, tw, mk.gidx(w), mk.addr(w));
+            for (uint32_t w = tid; w < total; w += nth) ntt_stage_c<K, LB, DIF, TWS>(s, tw, mk.gidx(w), mk.addr(w));
             __syncthreads();
-            NttStages<LOGL, LOW, DIF, DONE + K>::run(s, tw, tid, nth, nbatch_shift, mk);
+            NttStages<LOGL, LOW, DIF, DONE + K, TWS>::run(s, tw, tid, nth, nbatch_shift, mk);
         }
     }
 };
@@ -328,6 +329,21 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// TMA (cp.async.bulk, SASS UBLKCP) staging of a contiguous global table into shared memory, completion on an mbarrier.
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(mbar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* mbar) {
+    const unsigned m = (unsigned)__cvta_generic_to_shared(mbar), d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gsrc), "r"(bytes), "r"(m) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+    const unsigned m = (unsigned)__cvta_generic_to_shared(mbar);
+    asm volatile("{\n\t.reg .pred p;\n\tB200_MBAR_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra B200_MBAR_DONE;\n\tbra B200_MBAR_WAIT;\n\tB200_MBAR_DONE:\n\t}" ::"r"(m), "r"(parity) : "memory");
+}
+
 template <int LOGL, bool DIF>
 __global__ void __launch_bounds__(512) k_ntt_strided_p(uint32_t* __restrict__ data, uint32_t row_stride, uint32_t tiles_per_poly,
                                                        uint32_t num_tiles, size_t poly_stride, const uint32_t* __restrict__ tw_g,
@@ -337,6 +353,12 @@ __global__ void __launch_bounds__(512) k_ntt_strided_p(uint32_t* __restrict__ da
     const uint32_t tid = threadIdx.x, nth = blockDim.x;
     const uint32_t h = (lg_m + 1) / 2, lmask = (1u << h) - 1, mmask = (1u << lg_m) - 1;
     const uint32_t* plo = pow_g; const uint32_t* phi = pow_g + (1u << h);
+    // stage twiddles (L words) live behind the two tile buffers; one TMA bulk copy per CTA, awaited before the first stage
+    uint32_t* tw_s = smem + 2 * TILE;
+    __shared__ __align__(8) uint64_t tw_bar;
+    if (tid == 0) mbar_init(&tw_bar, 1);
+    __syncthreads();
+    if (tid == 0) tma_load_1d(tw_s, tw_g, L * 4, &tw_bar);
     auto tile_ptr = [&](uint32_t tile) { return data + (size_t)(tile / tiles_per_poly) * poly_stride + (size_t)(tile % tiles_per_poly) * 8; };
     auto issue_load = [&](uint32_t tile, uint32_t* buf) {
         const uint32_t* g = tile_ptr(tile);
@@ -346,13 +368,14 @@ __global__ void __launch_bounds__(512) k_ntt_strided_p(uint32_t* __restrict__ da
     uint32_t cur = 0;
     uint32_t tile = blockIdx.x;
     if (tile < num_tiles) issue_load(tile, smem);
+    mbar_wait(&tw_bar, 0);
     for (; tile < num_tiles; tile += gridDim.x) {
         uint32_t* buf = smem + cur * TILE;
         const uint32_t next = tile + gridDim.x;
         if (next < num_tiles) { issue_load(next, smem + (cur ^ 1) * TILE); cp_async_wait<1>(); }
         else cp_async_wait<0>();
         __syncthreads();
-        NttStages<LOGL, 0, DIF>::run(buf, tw_g, tid, nth, 3, MkStridedPad8{});
+        NttStages<LOGL, 0, DIF, 0, true>::run(buf, tw_s, tid, nth, 3, MkStridedPad8{});
         uint32_t* g = data + (size_t)(tile / tiles_per_poly) * poly_stride + (size_t)(tile % tiles_per_poly) * 8;
         const uint32_t col0 = (tile % tiles_per_poly) * 8;
         for (uint32_t ch = tid; ch < 2 * L; ch += nth) {
@@ -481,7 +504,7 @@ static cudaError_t run_strided(const DeviceTables* T, uint32_t* d, uint32_t logL
     if (logL >= 6 && logL <= 11 && ncols % 8 == 0 && row_stride % 4 == 0 && poly_stride % 4 == 0 && ((uintptr_t)d & 15) == 0 &&
         env_int("B200_NTT_PERSISTENT", 1)) {
         // persistent double-buffered kernel: 2 x (L x 8 words) of shared memory per CTA
-        const size_t sm = (size_t)2 * (((size_t)8 << logL) + ((size_t)8 << logL) / 16) * 4;
+        const size_t sm = (size_t)2 * (((size_t)8 << logL) + ((size_t)8 << logL) / 16) * 4 + ((size_t)4 << logL);
         const uint32_t tpp = ncols / 8, num_tiles = tpp * count;
         uint32_t per_sm = (uint32_t)(226 * 1024 / (sm + 1024)); if (per_sm > 4) per_sm = 4; if (per_sm < 1) per_sm = 1;
         uint32_t grid = (uint32_t)T->sm_count * per_sm; if (grid > num_tiles) grid = num_tiles;

@@ -19,6 +19,20 @@ namespace b200 {
 static __constant__ uint32_t c_rc[213] = B200_P2_RC_INIT;      // Montgomery form
 static __constant__ uint32_t c_diag[24] = B200_P2_DIAG_INIT;   // Montgomery form
 
+// fp_add written so that ptxas cannot encode the sum as IMAD.IADD (multiplier pipe): both halves are VIADDMNMX (ALU pipe).
+// Which adds of the linear layers use it is a measured trade-off (B200_P2_V, tools/microbench.cu).
+#ifndef B200_P2_V
+#define B200_P2_V 0
+#endif
+__device__ __forceinline__ uint32_t fp_add_alu(uint32_t a, uint32_t b) {
+    uint32_t s = addmin(a, b, 0xffffffffu);
+    return addmin(s, 0u - P, s);
+}
+#define P2_ADD_M4(a, b)  ((B200_P2_V & 1) ? fp_add_alu(a, b) : fp_add(a, b))
+#define P2_ADD_SUM(a, b) ((B200_P2_V & 2) ? fp_add_alu(a, b) : fp_add(a, b))
+#define P2_ADD_FIN(a, b) ((B200_P2_V & 4) ? fp_add_alu(a, b) : fp_add(a, b))
+#define P2_ADD_INT(a, b) ((B200_P2_V & 8) ? fp_add_alu(a, b) : fp_add(a, b))
+
 __device__ __forceinline__ uint32_t p2_sbox(uint32_t x) {
     uint32_t x2 = fp_mul(x, x);
     uint32_t x3 = fp_mul(x2, x);
@@ -31,36 +45,37 @@ __device__ __forceinline__ void p2_m_ext(uint32_t (&c)[24]) {
 #pragma unroll
     for (int k = 0; k < 6; k++) {
         uint32_t x0 = c[4 * k], x1 = c[4 * k + 1], x2 = c[4 * k + 2], x3 = c[4 * k + 3];
-        uint32_t t0 = fp_add(x0, x1), t1 = fp_add(x2, x3);
-        uint32_t t2 = fp_add(fp_dbl(x1), t1), t3 = fp_add(fp_dbl(x3), t0);
-        uint32_t t4 = fp_add(fp_dbl(fp_dbl(t1)), t3), t5 = fp_add(fp_dbl(fp_dbl(t0)), t2);
-        c[4 * k] = fp_add(t3, t5);
+        uint32_t t0 = P2_ADD_M4(x0, x1), t1 = P2_ADD_M4(x2, x3);
+        uint32_t t2 = P2_ADD_M4(P2_ADD_M4(x1, x1), t1), t3 = P2_ADD_M4(P2_ADD_M4(x3, x3), t0);
+        uint32_t t1_2 = P2_ADD_M4(t1, t1), t0_2 = P2_ADD_M4(t0, t0);
+        uint32_t t4 = P2_ADD_M4(P2_ADD_M4(t1_2, t1_2), t3), t5 = P2_ADD_M4(P2_ADD_M4(t0_2, t0_2), t2);
+        c[4 * k] = P2_ADD_M4(t3, t5);
         c[4 * k + 1] = t5;
-        c[4 * k + 2] = fp_add(t2, t4);
+        c[4 * k + 2] = P2_ADD_M4(t2, t4);
         c[4 * k + 3] = t4;
     }
     uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-        s0 = fp_add(s0, c[4 * k]); s1 = fp_add(s1, c[4 * k + 1]);
-        s2 = fp_add(s2, c[4 * k + 2]); s3 = fp_add(s3, c[4 * k + 3]);
+        s0 = P2_ADD_SUM(s0, c[4 * k]); s1 = P2_ADD_SUM(s1, c[4 * k + 1]);
+        s2 = P2_ADD_SUM(s2, c[4 * k + 2]); s3 = P2_ADD_SUM(s3, c[4 * k + 3]);
     }
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-        c[4 * k] = fp_add(c[4 * k], s0); c[4 * k + 1] = fp_add(c[4 * k + 1], s1);
-        c[4 * k + 2] = fp_add(c[4 * k + 2], s2); c[4 * k + 3] = fp_add(c[4 * k + 3], s3);
+        c[4 * k] = P2_ADD_FIN(c[4 * k], s0); c[4 * k + 1] = P2_ADD_FIN(c[4 * k + 1], s1);
+        c[4 * k + 2] = P2_ADD_FIN(c[4 * k + 2], s2); c[4 * k + 3] = P2_ADD_FIN(c[4 * k + 3], s3);
     }
 }
 
 // internal linear layer: c_i <- s + diag_i * c_i, s = sum c.
 // "+ s" rides in the IMAD.WIDE accumulator: X == s*2^32 (mod p) with hi(X) < p/2, so d*c + X < p*2^32.
 __device__ __forceinline__ void p2_m_int(uint32_t (&c)[24]) {
-    uint32_t a0 = fp_add(c[0], c[1]), a1 = fp_add(c[2], c[3]), a2 = fp_add(c[4], c[5]), a3 = fp_add(c[6], c[7]);
-    uint32_t a4 = fp_add(c[8], c[9]), a5 = fp_add(c[10], c[11]), a6 = fp_add(c[12], c[13]), a7 = fp_add(c[14], c[15]);
-    uint32_t a8 = fp_add(c[16], c[17]), a9 = fp_add(c[18], c[19]), a10 = fp_add(c[20], c[21]), a11 = fp_add(c[22], c[23]);
-    a0 = fp_add(a0, a1); a2 = fp_add(a2, a3); a4 = fp_add(a4, a5); a6 = fp_add(a6, a7); a8 = fp_add(a8, a9); a10 = fp_add(a10, a11);
-    a0 = fp_add(a0, a2); a4 = fp_add(a4, a6); a8 = fp_add(a8, a10);
-    uint32_t s = fp_add(fp_add(a0, a4), a8);
+    uint32_t a0 = P2_ADD_INT(c[0], c[1]), a1 = P2_ADD_INT(c[2], c[3]), a2 = P2_ADD_INT(c[4], c[5]), a3 = P2_ADD_INT(c[6], c[7]);
+    uint32_t a4 = P2_ADD_INT(c[8], c[9]), a5 = P2_ADD_INT(c[10], c[11]), a6 = P2_ADD_INT(c[12], c[13]), a7 = P2_ADD_INT(c[14], c[15]);
+    uint32_t a8 = P2_ADD_INT(c[16], c[17]), a9 = P2_ADD_INT(c[18], c[19]), a10 = P2_ADD_INT(c[20], c[21]), a11 = P2_ADD_INT(c[22], c[23]);
+    a0 = P2_ADD_INT(a0, a1); a2 = P2_ADD_INT(a2, a3); a4 = P2_ADD_INT(a4, a5); a6 = P2_ADD_INT(a6, a7); a8 = P2_ADD_INT(a8, a9); a10 = P2_ADD_INT(a10, a11);
+    a0 = P2_ADD_INT(a0, a2); a4 = P2_ADD_INT(a4, a6); a8 = P2_ADD_INT(a8, a10);
+    uint32_t s = P2_ADD_INT(P2_ADD_INT(a0, a4), a8);
     // X = s<<32 if s < (p+1)/2 else ((2s-p)<<31) = {hi: s-(p+1)/2, lo: 0x80000000}
     constexpr uint32_t HALF = (P + 1) / 2;
     bool big = s >= HALF;
