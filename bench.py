@@ -88,7 +88,7 @@ def reference_arm(args):
     os.environ["OMP_NUM_THREADS"] = str(cores)      # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host thread
     from oracle import pyoracle as o
     o.lib()
-    sample_po2 = 16
+    sample_po2 = 18
     for i in range(args.warmup):
         o.prove(sample_po2 - 2, 0xB2000000 + i)
     t0 = time.perf_counter()
@@ -346,7 +346,7 @@ def main():
             os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
             from oracle import pyoracle as o          # checker / CPU baseline leg only
             o.lib()
-            sample_po2 = 16
+            sample_po2 = 18
             o.prove(12, 1)
             t0 = time.perf_counter()
             seal = o.prove(sample_po2, 0xB2000000)

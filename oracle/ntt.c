@@ -80,6 +80,44 @@ static void fwd_butterfly(fp *io, unsigned n, unsigned expand_bits) {
     }
 }
 
+/* Same butterflies as rev_butterfly / fwd_butterfly, scheduled level-by-level so that ONE large transform can use every
+ * host thread (the batched entry points use it when there are fewer polynomials than threads; results are identical). */
+#define PAR_LEVELS 6
+static void rev_butterfly_par(fp *io, unsigned n) {
+    if (n <= PAR_LEVELS + 8) { rev_butterfly(io, n); return; }
+    for (unsigned lev = n; lev > n - PAR_LEVELS; lev--) {
+        const size_t half = (size_t)1 << (lev - 1), blocks = (size_t)1 << (n - lev);
+        const fp *tw = TW_REV[lev];
+#pragma omp parallel for schedule(static)
+        for (long t = 0; t < (long)(blocks * half); t++) {
+            size_t b = (size_t)t / half, i = (size_t)t % half;
+            fp *p = io + (b << lev);
+            fp a = p[i], c = p[i + half];
+            p[i] = fp_add(a, c);
+            p[i + half] = fp_mul(fp_sub(a, c), tw[i]);
+        }
+    }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long b = 0; b < (long)((size_t)1 << PAR_LEVELS); b++) rev_butterfly(io + ((size_t)b << (n - PAR_LEVELS)), n - PAR_LEVELS);
+}
+static void fwd_butterfly_par(fp *io, unsigned n, unsigned expand_bits) {
+    if (n <= PAR_LEVELS + 8 || n - PAR_LEVELS <= expand_bits) { fwd_butterfly(io, n, expand_bits); return; }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long b = 0; b < (long)((size_t)1 << PAR_LEVELS); b++) fwd_butterfly(io + ((size_t)b << (n - PAR_LEVELS)), n - PAR_LEVELS, expand_bits);
+    for (unsigned lev = n - PAR_LEVELS + 1; lev <= n; lev++) {
+        const size_t half = (size_t)1 << (lev - 1), blocks = (size_t)1 << (n - lev);
+        const fp *tw = TW_FWD[lev];
+#pragma omp parallel for schedule(static)
+        for (long t = 0; t < (long)(blocks * half); t++) {
+            size_t b = (size_t)t / half, i = (size_t)t % half;
+            fp *p = io + (b << lev);
+            fp a = p[i], c = fp_mul(p[i + half], tw[i]);
+            p[i] = fp_add(a, c);
+            p[i + half] = fp_sub(a, c);
+        }
+    }
+}
+
 void oracle_interpolate_ntt(fp *io, unsigned n) {
     oracle_ntt_prepare(n);
     rev_butterfly(io, n);
@@ -114,8 +152,20 @@ void oracle_bit_reverse(fp *io, unsigned n) {
 }
 
 /* batched forms (K1, K2, K3): `count` polynomials, column-major */
+static int few_polys(size_t count) { return count < 16; }     /* fewer polynomials than a typical host has threads */
+
 void oracle_batch_interpolate_ntt(fp *io, unsigned n, size_t count) {
     oracle_ntt_prepare(n);
+    if (few_polys(count)) {
+        fp norm = fp_inv(fp_from_u32(1u << n));
+        for (size_t c = 0; c < count; c++) {
+            fp *p = io + (c << n);
+            rev_butterfly_par(p, n);
+#pragma omp parallel for schedule(static)
+            for (long i = 0; i < (long)((size_t)1 << n); i++) p[i] = fp_mul(p[i], norm);
+        }
+        return;
+    }
 #pragma omp parallel for schedule(dynamic, 1)
     for (long c = 0; c < (long)count; c++) oracle_interpolate_ntt(io + ((size_t)c << n), n);
 }
@@ -130,6 +180,16 @@ void oracle_batch_evaluate_ntt(fp *io, unsigned n, size_t count) {
 }
 void oracle_batch_expand_into_evaluate_ntt(fp *out, const fp *in, unsigned n_in, size_t count, unsigned e) {
     oracle_ntt_prepare(n_in + e);
+    if (few_polys(count)) {
+        for (size_t c = 0; c < count; c++) {
+            fp *o = out + (c << (n_in + e));
+            const fp *src = in + (c << n_in);
+#pragma omp parallel for schedule(static)
+            for (long i = 0; i < (long)((size_t)1 << (n_in + e)); i++) o[i] = src[(size_t)i >> e];
+            fwd_butterfly_par(o, n_in + e, e);
+        }
+        return;
+    }
 #pragma omp parallel for schedule(dynamic, 1)
     for (long c = 0; c < (long)count; c++) {
         fp *o = out + ((size_t)c << (n_in + e));
