@@ -462,6 +462,184 @@ __global__ void __launch_bounds__(256) k_ntt_contig_c(uint32_t* out, const uint3
     }
 }
 
+
+// =========================================================================================================
+// Fused contiguous passes: the first transform stage reads straight from global memory (for the forward pass the x4
+// `expand` and the two lowest remaining levels are done in registers from a 16-byte load of 4 coefficients), the last
+// stage writes straight to global memory (with the inter-pass twiddle), so a row makes ONE shared-memory round trip
+// per middle stage instead of load + every stage + store.
+// =========================================================================================================
+template <int K, int LB, bool DIF, typename LD, typename ST>
+__device__ __forceinline__ void ntt_stage_io(const uint32_t* __restrict__ tw, uint32_t gidx, LD ld, ST st) {
+    constexpr int R = 1 << K;
+    constexpr uint32_t q = (1u << LB) >> K;
+    const uint32_t b = gidx >> (LB - K), o = gidx & (q - 1);
+    const uint32_t base = (b << LB) + o;
+    uint32_t x[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) x[j] = ld(base + j * q);
+    const uint32_t* twp = tw + o;
+#pragma unroll
+    for (int ll = 0; ll < K; ll++) {
+        const int l = DIF ? ll : (K - 1 - ll);
+        const int half = R >> (l + 1);
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            if ((j & half) == 0) {
+                const uint32_t w = __ldg(twp + ((1u << LB) >> (l + 1)) + (j & (half - 1)) * q);
+                const uint32_t a = x[j], bb = x[j + half];
+                if (DIF) { x[j] = fp_add(a, bb); x[j + half] = fp_mul(fp_sub(a, bb), w); }
+                else { const uint32_t t = fp_mul(bb, w); x[j] = fp_add(a, t); x[j + half] = fp_sub(a, t); }
+            }
+        }
+    }
+    st(base, x);
+}
+
+// forward pass 1: rows of Lin = Lc/4 bit-reversed coefficients -> Lc values (levels 3..LOGLC of the size-Lc DIT), times
+// w_M^(k * d1).  One work item of the head = 4 coefficients -> 16 consecutive positions (levels 3 and 4 in registers).
+template <int LOGLC>
+__global__ void __launch_bounds__(256) k_ntt_fwd1(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, uint32_t rows_per_cta, uint32_t lg_rpp,
+                                                  uint32_t total_rows, size_t in_poly_stride, size_t out_poly_stride,
+                                                  const uint32_t* __restrict__ tw_g, const uint32_t* __restrict__ pow_g, uint32_t lg_m,
+                                                  uint32_t lg_rows) {
+    extern __shared__ uint32_t smem[];
+    constexpr uint32_t Lc = 1u << LOGLC, Lin = Lc >> 2, rowpad = Lc + (Lc >> 4);
+    constexpr int NREM = LOGLC - 4;                 // levels 5..LOGLC
+    static_assert(NREM >= 4, "row too short for the fused kernel");
+    uint32_t* tile = smem;
+    const uint32_t tid = threadIdx.x, nth = blockDim.x;
+    const uint32_t row0 = blockIdx.x * rows_per_cta, rpp_mask = (1u << lg_rpp) - 1;
+    uint32_t nrows = total_rows - row0; if (nrows > rows_per_cta) nrows = rows_per_cta;
+    // ---- head: expand + levels 3,4 ----
+    {
+        const uint32_t w8_1 = __ldg(tw_g + 5), w8_2 = __ldg(tw_g + 6), w8_3 = __ldg(tw_g + 7);       // w_8^i  at tw[4+i]
+        uint32_t w16[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) w16[i] = __ldg(tw_g + 8 + i);                                       // w_16^i at tw[8+i]
+        for (uint32_t w = tid; w < nrows << (LOGLC - 4); w += nth) {
+            const uint32_t rr = w >> (LOGLC - 4), t = w & ((Lc >> 4) - 1), R = row0 + rr;
+            const uint4 c = *reinterpret_cast<const uint4*>(in + (size_t)(R >> lg_rpp) * in_poly_stride + (size_t)(R & rpp_mask) * Lin + 4 * t);
+            uint32_t y[16];
+            {   // level 3 on (c.x, c.y) -> y[0..7], on (c.z, c.w) -> y[8..15]
+                const uint32_t b1 = fp_mul(c.y, w8_1), b2 = fp_mul(c.y, w8_2), b3 = fp_mul(c.y, w8_3);
+                y[0] = fp_add(c.x, c.y); y[4] = fp_sub(c.x, c.y);
+                y[1] = fp_add(c.x, b1);  y[5] = fp_sub(c.x, b1);
+                y[2] = fp_add(c.x, b2);  y[6] = fp_sub(c.x, b2);
+                y[3] = fp_add(c.x, b3);  y[7] = fp_sub(c.x, b3);
+                const uint32_t d1 = fp_mul(c.w, w8_1), d2 = fp_mul(c.w, w8_2), d3 = fp_mul(c.w, w8_3);
+                y[8] = fp_add(c.z, c.w);  y[12] = fp_sub(c.z, c.w);
+                y[9] = fp_add(c.z, d1);   y[13] = fp_sub(c.z, d1);
+                y[10] = fp_add(c.z, d2);  y[14] = fp_sub(c.z, d2);
+                y[11] = fp_add(c.z, d3);  y[15] = fp_sub(c.z, d3);
+            }
+            uint32_t* dst = tile + rr * rowpad + 17 * t;        // phys(16t + j) = 16t + j + t
+#pragma unroll
+            for (int i = 0; i < 8; i++) {                        // level 4
+                const uint32_t bb = i == 0 ? y[8] : fp_mul(y[8 + i], w16[i]);
+                dst[i] = fp_add(y[i], bb);
+                dst[8 + i] = fp_sub(y[i], bb);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- middle stages (shared -> shared): remainder first, then radix-16 stages, leaving one radix-16 stage for the output ----
+    constexpr int KA = NREM % 4;                                  // 0..3
+    constexpr int NMID4 = (NREM - KA) / 4 - 1;                    // number of full middle stages
+    if constexpr (KA > 0) {
+        for (uint32_t w = tid; w < nrows << (LOGLC - KA); w += nth)
+            ntt_stage_c<KA, 4 + KA, false>(tile, tw_g, w & ((1u << (LOGLC - KA)) - 1), AddrContig{(w >> (LOGLC - KA)) * rowpad});
+        __syncthreads();
+    }
+    if constexpr (NMID4 >= 1) {
+        for (uint32_t w = tid; w < nrows << (LOGLC - 4); w += nth)
+            ntt_stage_c<4, 4 + KA + 4, false>(tile, tw_g, w & ((1u << (LOGLC - 4)) - 1), AddrContig{(w >> (LOGLC - 4)) * rowpad});
+        __syncthreads();
+    }
+    static_assert(NMID4 <= 1, "row too long for the fused kernel");
+    // ---- last stage (levels LOGLC-3..LOGLC) straight to global, times the inter-pass twiddle ----
+    const uint32_t h = (lg_m + 1) / 2, lmask = (1u << h) - 1, mmask = (1u << lg_m) - 1;
+    const uint32_t* plo = pow_g; const uint32_t* phi = pow_g + (1u << h);
+    for (uint32_t w = tid; w < nrows << (LOGLC - 4); w += nth) {
+        const uint32_t rr = w >> (LOGLC - 4), R = row0 + rr, rho = R & rpp_mask;
+        const uint32_t* trow = tile + rr * rowpad;
+        uint32_t* orow = out + (size_t)(R >> lg_rpp) * out_poly_stride + (size_t)rho * Lc;
+        const uint32_t d1 = pow_g ? bitrev(rho, lg_rows) : 0u;
+        ntt_stage_io<4, LOGLC, false>(tw_g, w & ((1u << (LOGLC - 4)) - 1),
+            [&](uint32_t pos) { return trow[pos + (pos >> 4)]; },
+            [&](uint32_t base, const uint32_t (&x)[16]) {
+                constexpr uint32_t q = Lc >> 4;
+                uint32_t e = (base * d1) & mmask;
+                const uint32_t estep = (q * d1) & mmask;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    uint32_t v = x[j];
+                    if (pow_g) { v = fp_mul(v, fp_mul(__ldg(plo + (e & lmask)), __ldg(phi + (e >> h)))); e = (e + estep) & mmask; }
+                    orow[base + j * q] = v;
+                }
+            });
+    }
+}
+
+// inverse pass B: contiguous rows of Lc values, DIF levels LOGLC..1, in place (out == in allowed), optional scale.
+template <int LOGLC>
+__global__ void __launch_bounds__(256) k_ntt_invb(uint32_t* out, const uint32_t* in, uint32_t rows_per_cta, uint32_t lg_rpp, uint32_t total_rows,
+                                                  size_t in_poly_stride, size_t out_poly_stride, const uint32_t* __restrict__ tw_g,
+                                                  uint32_t scale) {
+    extern __shared__ uint32_t smem[];
+    constexpr uint32_t Lc = 1u << LOGLC, rowpad = Lc + (Lc >> 4);
+    constexpr int REM = LOGLC - 4;                   // levels after the first radix-16 stage
+    constexpr int KF = (REM % 4) ? (REM % 4) : 4;    // final stage radix (1..4), written as vectors of 2^KF consecutive words
+    constexpr int NMID4 = (REM - KF) / 4;
+    static_assert(REM >= 1 && NMID4 <= 2, "unsupported row length");
+    uint32_t* tile = smem;
+    const uint32_t tid = threadIdx.x, nth = blockDim.x;
+    const uint32_t row0 = blockIdx.x * rows_per_cta, rpp_mask = (1u << lg_rpp) - 1;
+    uint32_t nrows = total_rows - row0; if (nrows > rows_per_cta) nrows = rows_per_cta;
+    // ---- first stage: global -> registers -> shared ----
+    for (uint32_t w = tid; w < nrows << (LOGLC - 4); w += nth) {
+        const uint32_t rr = w >> (LOGLC - 4), R = row0 + rr;
+        const uint32_t* irow = in + (size_t)(R >> lg_rpp) * in_poly_stride + (size_t)(R & rpp_mask) * Lc;
+        uint32_t* trow = tile + rr * rowpad;
+        ntt_stage_io<4, LOGLC, true>(tw_g, w & ((1u << (LOGLC - 4)) - 1),
+            [&](uint32_t pos) { return irow[pos]; },
+            [&](uint32_t base, const uint32_t (&x)[16]) {
+                constexpr uint32_t q = Lc >> 4;
+#pragma unroll
+                for (int j = 0; j < 16; j++) { const uint32_t pos = base + j * q; trow[pos + (pos >> 4)] = x[j]; }
+            });
+    }
+    __syncthreads();
+    if constexpr (NMID4 >= 1) {
+        for (uint32_t w = tid; w < nrows << (LOGLC - 4); w += nth)
+            ntt_stage_c<4, LOGLC - 4, true>(tile, tw_g, w & ((1u << (LOGLC - 4)) - 1), AddrContig{(w >> (LOGLC - 4)) * rowpad});
+        __syncthreads();
+    }
+    if constexpr (NMID4 >= 2) {
+        for (uint32_t w = tid; w < nrows << (LOGLC - 4); w += nth)
+            ntt_stage_c<4, LOGLC - 8, true>(tile, tw_g, w & ((1u << (LOGLC - 4)) - 1), AddrContig{(w >> (LOGLC - 4)) * rowpad});
+        __syncthreads();
+    }
+    // ---- final stage: shared -> registers -> global, 2^KF consecutive words per work item ----
+    for (uint32_t w = tid; w < nrows << (LOGLC - KF); w += nth) {
+        const uint32_t rr = w >> (LOGLC - KF), R = row0 + rr;
+        const uint32_t* trow = tile + rr * rowpad;
+        uint32_t* orow = out + (size_t)(R >> lg_rpp) * out_poly_stride + (size_t)(R & rpp_mask) * Lc;
+        ntt_stage_io<KF, KF, true>(tw_g, w & ((1u << (LOGLC - KF)) - 1),
+            [&](uint32_t pos) { return trow[pos + (pos >> 4)]; },
+            [&](uint32_t base, const uint32_t (&x)[1 << KF]) {
+                uint32_t v[1 << KF];
+#pragma unroll
+                for (int j = 0; j < (1 << KF); j++) v[j] = scale ? fp_mul(x[j], scale) : x[j];
+                if constexpr (KF == 1) *reinterpret_cast<uint2*>(orow + base) = make_uint2(v[0], v[1]);
+                else {
+#pragma unroll
+                    for (int j = 0; j < (1 << KF); j += 4) *reinterpret_cast<uint4*>(orow + base + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            });
+    }
+}
+
 __global__ void k_zk_shift(uint32_t* __restrict__ io, uint32_t lg_n, size_t total, const uint32_t* __restrict__ p3lo,
                            const uint32_t* __restrict__ p3hi) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -542,6 +720,20 @@ static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32
     const uint32_t grid = (uint32_t)((total_rows + rpc - 1) / rpc);
     const uint32_t* twt = DIF ? T->tw_inv : T->tw_fwd;
     uint32_t lg_rpp = 0; while ((1u << lg_rpp) < rows_per_poly) lg_rpp++;
+    if (logLc >= 8 && logLc <= 13 && (DIF ? lg_e == 0 : lg_e == 2) && (1u << lg_rpp) == rows_per_poly && env_int("B200_NTT_FUSED", 1) &&
+        (((uintptr_t)in | (uintptr_t)out) & 15) == 0 && in_stride % 4 == 0 && out_stride % 4 == 0 && (DIF || pow_g || true)) {
+        const size_t sm = (size_t)rpc * (Lc + (Lc >> 4)) * 4;
+#define B200_FUSED_CASE(LL) case LL: { cudaError_t e; \
+            if (DIF) { auto kf = k_ntt_invb<LL>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
+                if (pow_g) break; \
+                B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, scale); } \
+            else { auto kf = k_ntt_fwd1<LL>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
+                if (scale) break; \
+                B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, pow_g, lg_m, lg_rows); } \
+            return cudaGetLastError(); }
+        switch (logLc) { B200_FUSED_CASE(8) B200_FUSED_CASE(9) B200_FUSED_CASE(10) B200_FUSED_CASE(11) B200_FUSED_CASE(12) B200_FUSED_CASE(13) default: break; }
+#undef B200_FUSED_CASE
+    }
     if (logLc >= 8 && logLc <= 13 && (DIF ? lg_e == 0 : lg_e == 2) && (1u << lg_rpp) == rows_per_poly) {
         const size_t sm = (size_t)rpc * (Lc + (Lc >> 4)) * 4;
 #define B200_CONTIG_CASE(LL) case LL: { auto kc = k_ntt_contig_c<LL, DIF ? 0 : 2, DIF>; \
@@ -579,7 +771,9 @@ cudaError_t launch_batch_expand_ntt(const DeviceTables* T, uint32_t* d_out, cons
                                     uint32_t count, cudaStream_t s) {
     if (count == 0) return cudaSuccess;
     const uint32_t lg_m = lg_n + lg_e;
-    if (lg_m > MAX_LG + 2 || lg_m == 0) return cudaErrorInvalidValue;
+    if (lg_m == 0)        // size-1 transforms are the identity
+        return d_out == d_in ? cudaSuccess : cudaMemcpyAsync(d_out, d_in, (size_t)count * 4, cudaMemcpyDeviceToDevice, s);
+    if (lg_m > MAX_LG + 2) return cudaErrorInvalidValue;
     const size_t N = (size_t)1 << lg_n, M = (size_t)1 << lg_m;
     if (lg_m <= 13) return run_contig<false>(T, d_out, d_in, lg_m, lg_e, 1, count, N, M, nullptr, 0, 0, 0, s);
     if (lg_m > MAX_LG) return cudaErrorInvalidValue;

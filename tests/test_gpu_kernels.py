@@ -201,6 +201,28 @@ def test_batch_evaluate_any(gpu, b200lib, oracle, lg_n, count):
     assert np.array_equal(host(d_out).reshape(count, 4), oracle.batch_evaluate_any(co, lg_n, count, x))
 
 
+def test_empty_and_out_of_range_inputs(gpu, b200lib, oracle):
+    """Empty batches are no-ops, out-of-range sizes are reported as errors (never a crash, never a CPU fallback)."""
+    torch = gpu
+    d = torch.zeros(64, dtype=torch.int32, device="cuda")
+    for fn in (b200lib.b200_batch_intt, b200lib.b200_batch_ntt, b200lib.b200_batch_zk_shift, b200lib.b200_batch_bit_reverse):
+        ck(fn(ptr(d), 4, 0, None))                       # count == 0
+    ck(b200lib.b200_batch_expand_ntt(ptr(d), ptr(d), 4, 2, 0, None))
+    ck(b200lib.b200_poseidon2_rows(ptr(d), ptr(d), 0, 16, None))        # rows == 0
+    ck(b200lib.b200_poseidon2_fold(ptr(d), ptr(d), 0, None))
+    ck(b200lib.b200_fri_fold(ptr(d), ptr(d), 8, ptr(d), None))          # fewer than 16 coefficients: nothing to fold
+    torch.cuda.synchronize()
+    assert int(d.abs().sum()) == 0
+    assert b200lib.b200_batch_intt(ptr(d), 25, 1, None) is not None     # > 2^24
+    assert b200lib.b200_batch_expand_ntt(ptr(d), ptr(d), 23, 2, 1, None) is not None
+    assert b200lib.b200_merkle_tree(ptr(d), ptr(d), 27, 1, None) is not None
+    # size-1 transforms are the identity
+    one = dev(torch, oracle.to_mont(np.array([5, 7, 11])))
+    ck(b200lib.b200_batch_intt(ptr(one), 0, 3, None)); ck(b200lib.b200_batch_ntt(ptr(one), 0, 3, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(host(one), oracle.to_mont(np.array([5, 7, 11])))
+
+
 def test_stream_argument(gpu, b200lib, oracle):
     """Entry points honour the caller's stream (the agent passes its own): run on a side stream."""
     torch = gpu
