@@ -6,9 +6,9 @@
 // overwrite-mode sponge (rate 16) over a column-major matrix, hash_pair for interior nodes, nodes[1] = root.
 //
 // B200 notes: leaf hashing is INT32-pipe bound (1356 Montgomery multiplies per permutation), not HBM bound;
-// one thread owns one row so that a warp reads 128 contiguous bytes per column, and the next 16-column chunk is
-// prefetched into registers while the current permutation runs.  The transcript lives in device memory so a
-// whole proof is enqueued without a host round trip (CUDA-graph friendly).
+// one thread owns one row so that a warp reads 128 contiguous bytes per column (DRAM traffic = 1.001x the algorithmic
+// bytes, profiles/traffic_r01.json); 16 loads are in flight per thread before each permutation.  The transcript lives in
+// device memory so a whole proof is enqueued without a host round trip (CUDA-graph friendly).
 #include "internal.h"
 #include "poseidon2.cuh"
 #include <cstdlib>

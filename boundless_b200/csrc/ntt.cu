@@ -15,8 +15,13 @@
 //                  the blow-up) -> inter-pass twiddle -> written as a row of 4*N2;
 //          pass 2  strided tile, DIT along rows, in place.
 // Every pass moves each element HBM->smem->HBM once with >=32-byte runs; butterflies are radix-16 register
-// stages (4 levels per shared-memory round trip); stage twiddles come from a compact per-level table staged
-// in shared memory, inter-pass twiddles from a two-table decomposition w^e = lo[e & mask] * hi[e >> h].
+// stages (4 levels per shared-memory round trip); stage twiddles come from one compact per-level table
+// (TMA-staged into shared memory in the persistent strided pass, read-only path elsewhere), inter-pass twiddles
+// from a two-table decomposition w^e = lo[e & mask] * hi[e >> h].
+// Kernel families, fastest first (the host dispatch falls through to the next when a shape is not covered):
+//   k_ntt_strided_p / k_ntt_fwd1 / k_ntt_invb   compile-time sizes, persistent + double-buffered / fused passes
+//   k_ntt_strided_c / k_ntt_contig_c            compile-time sizes, one tile per CTA
+//   k_ntt_strided   / k_ntt_contig              runtime sizes (any 2^k)
 #include "internal.h"
 #include "field.cuh"
 #include <cstdlib>
@@ -721,7 +726,7 @@ static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32
     const uint32_t* twt = DIF ? T->tw_inv : T->tw_fwd;
     uint32_t lg_rpp = 0; while ((1u << lg_rpp) < rows_per_poly) lg_rpp++;
     if (logLc >= 8 && logLc <= 13 && (DIF ? lg_e == 0 : lg_e == 2) && (1u << lg_rpp) == rows_per_poly && env_int("B200_NTT_FUSED", 1) &&
-        (((uintptr_t)in | (uintptr_t)out) & 15) == 0 && in_stride % 4 == 0 && out_stride % 4 == 0 && (DIF || pow_g || true)) {
+        (((uintptr_t)in | (uintptr_t)out) & 15) == 0 && in_stride % 4 == 0 && out_stride % 4 == 0) {
         const size_t sm = (size_t)rpc * (Lc + (Lc >> 4)) * 4;
 #define B200_FUSED_CASE(LL) case LL: { cudaError_t e; \
             if (DIF) { auto kf = k_ntt_invb<LL>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
