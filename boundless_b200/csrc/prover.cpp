@@ -377,9 +377,9 @@ const char* b200_recursion_async(b200_prover* p, uint32_t slot, const b200_circu
 const char* b200_prover_wait(b200_prover* p, uint32_t slot) {
     if (!p || slot >= p->slots.size()) { set_error("b200: bad prover/slot"); return last_error(); }
     Slot& s = p->slots[slot];
+    s.busy = false;                       // whatever happens below, the slot is reusable afterwards
     CU(cudaSetDevice(p->device));
     CU(cudaStreamSynchronize(s.stream));
-    s.busy = false;
     return nullptr;
 }
 

@@ -77,3 +77,10 @@ def test_constants_match_independent_generators(b200lib, oracle):
     assert fwd[27] == 137 and fwd[1] == oracle.P - 1 and fwd[0] == 1
     for k in range(28):
         assert int(fwd[k]) == oracle.from_mont(np.array([L.oracle_rou_fwd(k)], dtype=np.uint32))[0]
+
+
+def test_rust_sys_binding_declares_the_same_symbols():
+    """bindings/rust/b200zkp-sys (source only; no cargo here) must list exactly the functions of include/b200zkp.h."""
+    src = open(os.path.join(ROOT, "bindings", "rust", "b200zkp-sys", "src", "lib.rs")).read()
+    rust = sorted(set(re.findall(r"pub fn (b200_[a-z0-9_]+)\s*\(", src)))
+    assert rust == header_functions()

@@ -128,3 +128,16 @@ def test_full_size_segment_verifies(gpu, oracle):
         assert oracle.verify(l0.seal) == 0
     finally:
         srv.close()
+
+
+def test_po2_21_segment_verifies(gpu, oracle):
+    """compose.yml:67 runs the agents with --segment-po2 21: one 2^21-row segment (twice BASELINE config 2; 2^23-point evaluation
+    domain, 2^23-leaf Merkle trees, the 2^23 check-polynomial iNTT) must pass the oracle's verifier."""
+    from boundless_b200 import ProverOpts, Segment, VerifierContext, get_prover_server
+    srv = get_prover_server(ProverOpts(segment_po2=21, recursion_po2=18, slots=1))
+    try:
+        r = srv.prove_segment(VerifierContext(), Segment(index=3, po2=21))
+        assert r.seal.size == oracle.seal_words(21)
+        assert oracle.verify(r.seal) == 0
+    finally:
+        srv.close()
