@@ -238,7 +238,8 @@ def main():
         barrier()
         t0 = time.perf_counter()
         root, stats = prove_job(n_seg, prove_and_lift, srv.join, lambda r: r.seal, lambda sl, c: SuccinctReceipt(sl, 2, c), rec_words,
-                                device=torch.device("cuda", local_rank))
+                                device=torch.device("cuda", local_rank),
+                                prove_and_lift_many=lambda idx: srv.prove_and_lift_many([Segment(index=i, po2=PO2) for i in idx]))
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt, float(stats["bytes_sent"])], dtype=torch.float64, device="cuda")

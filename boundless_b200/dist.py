@@ -72,11 +72,14 @@ class _Comm:
 
 def prove_job(n_segments: int, prove_and_lift: Callable[[int], object], join: Callable[[object, object], object],
               seal_of: Callable[[object], np.ndarray], receipt_from_seal: Callable[[np.ndarray, tuple], object],
-              recursion_seal_words: int, device=None, root_rank: int = 0):
+              recursion_seal_words: int, device=None, root_rank: int = 0,
+              prove_and_lift_many: Optional[Callable[[List[int]], List[object]]] = None):
     """Run the whole job DAG.  Every rank calls this with the same arguments.
 
     prove_and_lift(i)  -> lifted receipt of segment i (ProverServer.prove_segment + lift, tasks/prove.rs:44-104)
     join(a, b)         -> joined receipt                  (tasks/join.rs:52-56)
+    prove_and_lift_many(indices) -> receipts: optional batched form (lets the caller keep several proofs in flight); the
+                          segment tasks have no prerequisites (tasks/executor.rs:86-120), so a rank may run all of its own first.
     Returns (root receipt on `root_rank` else None, stats dict)."""
     comm = _Comm(device)
     tasks = plan_job(n_segments)
@@ -98,9 +101,14 @@ def prove_job(n_segments: int, prove_and_lift: Callable[[int], object], join: Ca
     have = {}
     stats = {"proved": 0, "joined": 0, "sent": 0, "received": 0}
     root = None
+    if prove_and_lift_many is not None:
+        mine = [t.task_number for t in tasks if t.command == CMD_SEGMENT and owner[t.task_number] == rank]
+        for tn, rcpt in zip(mine, prove_and_lift_many([seg_no[tn] for tn in mine])):
+            have[tn] = rcpt
+        stats["proved"] = len(mine)
     for t in tasks:
         if t.command == CMD_SEGMENT:
-            if owner[t.task_number] == rank:
+            if owner[t.task_number] == rank and t.task_number not in have:
                 have[t.task_number] = prove_and_lift(seg_no[t.task_number])
                 stats["proved"] += 1
         elif t.command == CMD_JOIN:

@@ -175,6 +175,26 @@ class ProverServer:
     def last_ms(self, slot):
         return float(self.L.b200_prover_last_ms(self.h, slot))
 
+    def prove_and_lift_many(self, segments):
+        """prove_segment + lift for a list of segments with every slot kept busy (tasks/prove.rs:44-104, pipelined):
+        proofs rotate over the slots; a finished segment proof is lifted on the slot it ran on."""
+        n, slots = len(segments), self.opts.slots
+        out = [None] * n
+        pending = []          # (slot, stage, index)
+        free = list(range(slots))
+        nxt = 0
+        while nxt < n or pending:
+            while free and nxt < n:
+                s = free.pop(0)
+                self.submit_segment(s, segments[nxt]); pending.append((s, "seg", nxt)); nxt += 1
+            s, stage, i = pending.pop(0)
+            r = self.wait(s)
+            if stage == "seg":
+                self.submit_recursion(s, KIND_LIFT, r); pending.append((s, "lift", i))
+            else:
+                out[i] = r; free.append(s)
+        return out
+
     # -- the reference's method names (synchronous, slot 0) -------------------------------------------------
     def prove_segment(self, ctx: VerifierContext, segment: Segment) -> SegmentReceipt:
         self.submit_segment(0, segment)

@@ -81,6 +81,11 @@ def test_job_dag_with_real_proofs(small_server, oracle):
                             small_server.seal_words(small_server._rec_circuit(KIND_LIFT)))
     assert stats == {"proved": 3, "joined": 2, "sent": 0, "received": 0, "bytes_sent": 0}
     assert root.claim == (0, 2)
+    # the batched / pipelined form (all slots busy) yields the same root
+    root2, _ = prove_job(3, None, small_server.join, lambda r: r.seal, lambda s, c: SuccinctReceipt(s, KIND_JOIN, c),
+                         small_server.seal_words(small_server._rec_circuit(KIND_LIFT)),
+                         prove_and_lift_many=lambda idx: small_server.prove_and_lift_many([Segment(index=i, po2=9) for i in idx]))
+    assert np.array_equal(root2.seal, root.seal)
     def rec(kind, digest):
         return oracle.prove(rp, int(digest[0]) | (int(digest[1]) << 32), *RECURSION_WIDTHS, kind=kind, input_digest=digest)
     lifts = [rec(KIND_LIFT, oracle.seal_digest(oracle.prove(9, 0xB2000000 + i))) for i in range(3)]
