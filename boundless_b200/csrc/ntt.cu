@@ -28,14 +28,21 @@
 
 namespace b200 {
 
+// Address functors: operator()(pos) is the general form; base(pos) + off(delta) is the split form the compile-time stages
+// use: for the stage gathers (delta = j*q with the group offset o < q) phys(base + delta) == base(base) + off(delta), and
+// off(delta) is an immediate, so a gather/scatter costs no address arithmetic per element.
 struct AddrStrided {
     uint32_t lgTW, t;
     __device__ __forceinline__ uint32_t operator()(uint32_t pos) const { return (pos << lgTW) + t; }
+    __device__ __forceinline__ uint32_t base(uint32_t pos) const { return (pos << lgTW) + t; }
+    __device__ __forceinline__ uint32_t off(uint32_t d) const { return d << lgTW; }
 };
 struct AddrContig {
     uint32_t base;
     // one pad word per 16 keeps the radix-16 gathers (stride q < 32) free of bank conflicts
     __device__ __forceinline__ uint32_t operator()(uint32_t pos) const { return base + pos + (pos >> 4); }
+    __device__ __forceinline__ uint32_t base_of(uint32_t pos) const { return base + pos + (pos >> 4); }
+    __device__ __forceinline__ static constexpr uint32_t off(uint32_t d) { return d + (d >> 4); }
 };
 
 // One radix-2^K register stage: gathers the 2^K elements base + j*q of the block of size 2^lb that contains them,
@@ -215,6 +222,9 @@ __global__ void __launch_bounds__(256) k_ntt_contig(uint32_t* __restrict__ out, 
 // Specialised (compile-time size) passes: all stage strides, twiddle offsets and loop counts are immediates,
 // tables are read through the read-only path (L1-resident, no per-CTA staging), so a CTA only stages its data tile.
 // =========================================================================================================
+template <typename A> __device__ __forceinline__ uint32_t addr_base(const A& a, uint32_t pos) { return a.base(pos); }
+__device__ __forceinline__ uint32_t addr_base(const AddrContig& a, uint32_t pos) { return a.base_of(pos); }
+
 template <int K, int LB, bool DIF, bool TWS = false, typename ADDR>
 __device__ __forceinline__ void ntt_stage_c(uint32_t* s, const uint32_t* __restrict__ tw, uint32_t gidx, ADDR addr) {
     constexpr int R = 1 << K;
@@ -223,7 +233,9 @@ __device__ __forceinline__ void ntt_stage_c(uint32_t* s, const uint32_t* __restr
     const uint32_t base = (b << LB) + o;
     uint32_t x[R];
 #pragma unroll
-    for (int j = 0; j < R; j++) x[j] = s[addr(base + j * q)];
+    const uint32_t a0 = addr_base(addr, base);
+#pragma unroll
+    for (int j = 0; j < R; j++) x[j] = s[a0 + addr.off(j * q)];
     const uint32_t* twp = tw + o;
 #pragma unroll
     for (int ll = 0; ll < K; ll++) {
@@ -247,7 +259,7 @@ __device__ __forceinline__ void ntt_stage_c(uint32_t* s, const uint32_t* __restr
         }
     }
 #pragma unroll
-    for (int j = 0; j < R; j++) s[addr(base + j * q)] = x[j];
+    for (int j = 0; j < R; j++) s[a0 + addr.off(j * q)] = x[j];
 }
 
 // runs all stages of a length-2^LOGL transform held in shared memory; LOW = number of already-done low levels (DIT expand)
@@ -271,6 +283,8 @@ struct NttStages {
 struct AddrStridedPad8 {   // 8-column tile, one padding row per 16 rows: groups of a warp that sit 16 rows apart hit different banks
     uint32_t t;
     __device__ __forceinline__ uint32_t operator()(uint32_t pos) const { return ((pos + (pos >> 4)) << 3) + t; }
+    __device__ __forceinline__ uint32_t base(uint32_t pos) const { return ((pos + (pos >> 4)) << 3) + t; }
+    __device__ __forceinline__ static constexpr uint32_t off(uint32_t d) { return (d + (d >> 4)) << 3; }
 };
 struct MkStridedPad8 {
     __device__ __forceinline__ uint32_t gidx(uint32_t w) const { return w >> 3; }
@@ -482,7 +496,7 @@ __device__ __forceinline__ void ntt_stage_io(const uint32_t* __restrict__ tw, ui
     const uint32_t base = (b << LB) + o;
     uint32_t x[R];
 #pragma unroll
-    for (int j = 0; j < R; j++) x[j] = ld(base + j * q);
+    for (int j = 0; j < R; j++) x[j] = ld(base, (uint32_t)(j * q));
     const uint32_t* twp = tw + o;
 #pragma unroll
     for (int ll = 0; ll < K; ll++) {
@@ -571,7 +585,7 @@ __global__ void __launch_bounds__(256) k_ntt_fwd1(uint32_t* __restrict__ out, co
         uint32_t* orow = out + (size_t)(R >> lg_rpp) * out_poly_stride + (size_t)rho * Lc;
         const uint32_t d1 = pow_g ? bitrev(rho, lg_rows) : 0u;
         ntt_stage_io<4, LOGLC, false>(tw_g, w & ((1u << (LOGLC - 4)) - 1),
-            [&](uint32_t pos) { return trow[pos + (pos >> 4)]; },
+            [&](uint32_t b0, uint32_t d) { return trow[(b0 + (b0 >> 4)) + (d + (d >> 4))]; },
             [&](uint32_t base, const uint32_t (&x)[16]) {
                 constexpr uint32_t q = Lc >> 4;
                 uint32_t e = (base * d1) & mmask;
@@ -607,11 +621,13 @@ __global__ void __launch_bounds__(256) k_ntt_invb(uint32_t* out, const uint32_t*
         const uint32_t* irow = in + (size_t)(R >> lg_rpp) * in_poly_stride + (size_t)(R & rpp_mask) * Lc;
         uint32_t* trow = tile + rr * rowpad;
         ntt_stage_io<4, LOGLC, true>(tw_g, w & ((1u << (LOGLC - 4)) - 1),
-            [&](uint32_t pos) { return irow[pos]; },
+            [&](uint32_t b0, uint32_t d) { return irow[b0 + d]; },
             [&](uint32_t base, const uint32_t (&x)[16]) {
                 constexpr uint32_t q = Lc >> 4;
 #pragma unroll
-                for (int j = 0; j < 16; j++) { const uint32_t pos = base + j * q; trow[pos + (pos >> 4)] = x[j]; }
+                const uint32_t pb = base + (base >> 4);
+#pragma unroll
+                for (int j = 0; j < 16; j++) trow[pb + AddrContig::off(j * q)] = x[j];
             });
     }
     __syncthreads();
@@ -631,7 +647,7 @@ __global__ void __launch_bounds__(256) k_ntt_invb(uint32_t* out, const uint32_t*
         const uint32_t* trow = tile + rr * rowpad;
         uint32_t* orow = out + (size_t)(R >> lg_rpp) * out_poly_stride + (size_t)(R & rpp_mask) * Lc;
         ntt_stage_io<KF, KF, true>(tw_g, w & ((1u << (LOGLC - KF)) - 1),
-            [&](uint32_t pos) { return trow[pos + (pos >> 4)]; },
+            [&](uint32_t b0, uint32_t d) { return trow[(b0 + (b0 >> 4)) + (d + (d >> 4))]; },
             [&](uint32_t base, const uint32_t (&x)[1 << KF]) {
                 uint32_t v[1 << KF];
 #pragma unroll
