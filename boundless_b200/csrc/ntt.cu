@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(256) k_ntt_contig_c(uint32_t* out, const uint3
 // stage writes straight to global memory (with the inter-pass twiddle), so a row makes ONE shared-memory round trip
 // per middle stage instead of load + every stage + store.
 // =========================================================================================================
-template <int K, int LB, bool DIF, typename LD, typename ST>
+template <int K, int LB, bool DIF, bool TWS = false, typename LD, typename ST>
 __device__ __forceinline__ void ntt_stage_io(const uint32_t* __restrict__ tw, uint32_t gidx, LD ld, ST st) {
     constexpr int R = 1 << K;
     constexpr uint32_t q = (1u << LB) >> K;
@@ -505,7 +505,8 @@ __device__ __forceinline__ void ntt_stage_io(const uint32_t* __restrict__ tw, ui
 #pragma unroll
         for (int j = 0; j < R; j++) {
             if ((j & half) == 0) {
-                const uint32_t w = __ldg(twp + ((1u << LB) >> (l + 1)) + (j & (half - 1)) * q);
+                const uint32_t* wp = twp + ((1u << LB) >> (l + 1)) + (j & (half - 1)) * q;
+                const uint32_t w = TWS ? *wp : __ldg(wp);
                 const uint32_t a = x[j], bb = x[j + half];
                 if (DIF) { x[j] = fp_add(a, bb); x[j + half] = fp_mul(fp_sub(a, bb), w); }
                 else { const uint32_t t = fp_mul(bb, w); x[j] = fp_add(a, t); x[j + half] = fp_sub(a, t); }
@@ -513,6 +514,72 @@ __device__ __forceinline__ void ntt_stage_io(const uint32_t* __restrict__ tw, ui
         }
     }
     st(base, x);
+}
+
+// Persistent strided pass, final stage fused with the global store: radix-16 stages run shared -> shared, the last
+// (remainder) stage goes shared -> registers -> global (with the inter-pass twiddle for the inverse transform), so a tile
+// makes one shared-memory round trip less and needs one barrier less than k_ntt_strided_p.
+template <int LOGL, bool DIF>
+__global__ void __launch_bounds__(512) k_ntt_strided_pf(uint32_t* __restrict__ data, uint32_t row_stride, uint32_t tiles_per_poly,
+                                                        uint32_t num_tiles, size_t poly_stride, const uint32_t* __restrict__ tw_g,
+                                                        const uint32_t* __restrict__ pow_g, uint32_t lg_m) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    constexpr uint32_t L = 1u << LOGL, TILE = (L + (L >> 4)) * 8;
+    constexpr int KF = (LOGL % 4) ? (LOGL % 4) : 4, NFULL = (LOGL - KF) / 4;
+    static_assert(NFULL >= 1 && NFULL <= 2, "unsupported tile height");
+    const uint32_t tid = threadIdx.x, nth = blockDim.x;
+    const uint32_t h = (lg_m + 1) / 2, lmask = (1u << h) - 1, mmask = (1u << lg_m) - 1;
+    const uint32_t* plo = pow_g; const uint32_t* phi = pow_g + (1u << h);
+    uint32_t* tw_s = smem + 2 * TILE;
+    __shared__ __align__(8) uint64_t tw_bar;
+    if (tid == 0) mbar_init(&tw_bar, 1);
+    __syncthreads();
+    if (tid == 0) tma_load_1d(tw_s, tw_g, L * 4, &tw_bar);
+    auto issue_load = [&](uint32_t tile, uint32_t* buf) {
+        const uint32_t* g = data + (size_t)(tile / tiles_per_poly) * poly_stride + (size_t)(tile % tiles_per_poly) * 8;
+        for (uint32_t ch = tid; ch < 2 * L; ch += nth) { const uint32_t r = ch >> 1; cp_async16(buf + (r + (r >> 4)) * 8 + (ch & 1) * 4, g + (size_t)r * row_stride + (ch & 1) * 4); }
+        cp_async_commit();
+    };
+    uint32_t cur = 0, tile = blockIdx.x;
+    if (tile < num_tiles) issue_load(tile, smem);
+    mbar_wait(&tw_bar, 0);
+    for (; tile < num_tiles; tile += gridDim.x) {
+        uint32_t* buf = smem + cur * TILE;
+        const uint32_t next = tile + gridDim.x;
+        if (next < num_tiles) { issue_load(next, smem + (cur ^ 1) * TILE); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        {
+            constexpr int LB1 = DIF ? LOGL : 4;
+            for (uint32_t w = tid; w < (L >> 4) * 8; w += nth) ntt_stage_c<4, LB1, DIF, true>(buf, tw_s, w >> 3, AddrStridedPad8{w & 7u});
+            __syncthreads();
+        }
+        if constexpr (NFULL >= 2) {
+            constexpr int LB2 = DIF ? LOGL - 4 : 8;
+            for (uint32_t w = tid; w < (L >> 4) * 8; w += nth) ntt_stage_c<4, LB2, DIF, true>(buf, tw_s, w >> 3, AddrStridedPad8{w & 7u});
+            __syncthreads();
+        }
+        uint32_t* g = data + (size_t)(tile / tiles_per_poly) * poly_stride + (size_t)(tile % tiles_per_poly) * 8;
+        const uint32_t col0 = (tile % tiles_per_poly) * 8;
+        constexpr int LBF = DIF ? KF : LOGL;
+        constexpr uint32_t QF = (1u << LBF) >> KF;
+        for (uint32_t w = tid; w < (L >> KF) * 8; w += nth) {
+            const uint32_t t = w & 7u;
+            ntt_stage_io<KF, LBF, DIF, true>(tw_s, w >> 3,
+                [&](uint32_t b0, uint32_t d) { return buf[((b0 + (b0 >> 4)) << 3) + t + ((d + (d >> 4)) << 3)]; },
+                [&](uint32_t base, const uint32_t (&x)[1 << KF]) {
+#pragma unroll
+                    for (int j = 0; j < (1 << KF); j++) {
+                        const uint32_t row = base + j * QF;
+                        uint32_t v = x[j];
+                        if (pow_g) { const uint32_t e = ((col0 + t) * bitrev(row, LOGL)) & mmask; v = fp_mul(v, fp_mul(__ldg(plo + (e & lmask)), __ldg(phi + (e >> h)))); }
+                        g[(size_t)row * row_stride + t] = v;
+                    }
+                });
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
 }
 
 // forward pass 1: rows of Lin = Lc/4 bit-reversed coefficients -> Lc values (levels 3..LOGLC of the size-Lc DIT), times
@@ -707,6 +774,11 @@ static cudaError_t run_strided(const DeviceTables* T, uint32_t* d, uint32_t logL
         const uint32_t tpp = ncols / 8, num_tiles = tpp * count;
         uint32_t per_sm = (uint32_t)(226 * 1024 / (sm + 1024)); if (per_sm > 4) per_sm = 4; if (per_sm < 1) per_sm = 1;
         uint32_t grid = (uint32_t)T->sm_count * per_sm; if (grid > num_tiles) grid = num_tiles;
+#define B200_STRIDED_PF_CASE(LL) case LL: { auto kp = k_ntt_strided_pf<LL, DIF>; \
+            cudaError_t e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
+            B200_LAUNCH(kp)<<<grid, env_int("B200_NTT_THREADS", 512), sm, s>>>(d, row_stride, tpp, num_tiles, poly_stride, twt, pow_g, lg_m); return cudaGetLastError(); }
+        if (env_int("B200_NTT_PF", 1)) switch (logL) { B200_STRIDED_PF_CASE(6) B200_STRIDED_PF_CASE(7) B200_STRIDED_PF_CASE(8) B200_STRIDED_PF_CASE(9) B200_STRIDED_PF_CASE(10) B200_STRIDED_PF_CASE(11) default: break; }
+#undef B200_STRIDED_PF_CASE
 #define B200_STRIDED_P_CASE(LL) case LL: { auto kp = k_ntt_strided_p<LL, DIF>; \
             cudaError_t e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
             B200_LAUNCH(kp)<<<grid, env_int("B200_NTT_THREADS", 512), sm, s>>>(d, row_stride, tpp, num_tiles, poly_stride, twt, pow_g, lg_m); return cudaGetLastError(); }
