@@ -584,21 +584,35 @@ __global__ void __launch_bounds__(512) k_ntt_strided_pf(uint32_t* __restrict__ d
 
 // forward pass 1: rows of Lin = Lc/4 bit-reversed coefficients -> Lc values (levels 3..LOGLC of the size-Lc DIT), times
 // w_M^(k * d1).  One work item of the head = 4 coefficients -> 16 consecutive positions (levels 3 and 4 in registers).
-template <int LOGLC>
-__global__ void __launch_bounds__(256) k_ntt_fwd1(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, uint32_t rows_per_cta, uint32_t lg_rpp,
+template <int LOGLC, int LGE>
+__global__ void __launch_bounds__(256) k_ntt_fwd1(uint32_t* out, const uint32_t* in, uint32_t rows_per_cta, uint32_t lg_rpp,
                                                   uint32_t total_rows, size_t in_poly_stride, size_t out_poly_stride,
                                                   const uint32_t* __restrict__ tw_g, const uint32_t* __restrict__ pow_g, uint32_t lg_m,
                                                   uint32_t lg_rows) {
     extern __shared__ uint32_t smem[];
-    constexpr uint32_t Lc = 1u << LOGLC, Lin = Lc >> 2, rowpad = Lc + (Lc >> 4);
+    static_assert(LGE == 0 || LGE == 2, "blow-up 1 or 4");
+    constexpr uint32_t Lc = 1u << LOGLC, Lin = Lc >> LGE, rowpad = Lc + (Lc >> 4);
     constexpr int NREM = LOGLC - 4;                 // levels 5..LOGLC
     static_assert(NREM >= 4, "row too short for the fused kernel");
     uint32_t* tile = smem;
     const uint32_t tid = threadIdx.x, nth = blockDim.x;
     const uint32_t row0 = blockIdx.x * rows_per_cta, rpp_mask = (1u << lg_rpp) - 1;
     uint32_t nrows = total_rows - row0; if (nrows > rows_per_cta) nrows = rows_per_cta;
-    // ---- head: expand + levels 3,4 ----
-    {
+    // ---- head: levels 1..4 of 16 consecutive positions, in registers ----
+    if constexpr (LGE == 0) {
+        for (uint32_t w = tid; w < nrows << (LOGLC - 4); w += nth) {
+            const uint32_t rr = w >> (LOGLC - 4), t = w & ((Lc >> 4) - 1), R = row0 + rr;
+            const uint4* src = reinterpret_cast<const uint4*>(in + (size_t)(R >> lg_rpp) * in_poly_stride + (size_t)(R & rpp_mask) * Lin + 16 * t);
+            const uint4 c0 = src[0], c1 = src[1], c2 = src[2], c3 = src[3];
+            const uint32_t c[16] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w};
+            uint32_t* dst = tile + rr * rowpad + 17 * t;
+            ntt_stage_io<4, 4, false>(tw_g, 0u, [&](uint32_t, uint32_t d) { return c[d]; },
+                                      [&](uint32_t, const uint32_t (&x)[16]) {
+#pragma unroll
+                                          for (int j = 0; j < 16; j++) dst[j] = x[j];
+                                      });
+        }
+    } else {   // expand x4 + levels 3,4
         const uint32_t w8_1 = __ldg(tw_g + 5), w8_2 = __ldg(tw_g + 6), w8_3 = __ldg(tw_g + 7);       // w_8^i  at tw[4+i]
         uint32_t w16[8];
 #pragma unroll
@@ -813,14 +827,17 @@ static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32
     const uint32_t grid = (uint32_t)((total_rows + rpc - 1) / rpc);
     const uint32_t* twt = DIF ? T->tw_inv : T->tw_fwd;
     uint32_t lg_rpp = 0; while ((1u << lg_rpp) < rows_per_poly) lg_rpp++;
-    if (logLc >= 8 && logLc <= 13 && (DIF ? lg_e == 0 : lg_e == 2) && (1u << lg_rpp) == rows_per_poly && env_int("B200_NTT_FUSED", 1) &&
+    if (logLc >= 8 && logLc <= 13 && (DIF ? lg_e == 0 : (lg_e == 2 || lg_e == 0)) && (1u << lg_rpp) == rows_per_poly && env_int("B200_NTT_FUSED", 1) &&
         (((uintptr_t)in | (uintptr_t)out) & 15) == 0 && in_stride % 4 == 0 && out_stride % 4 == 0) {
         const size_t sm = (size_t)rpc * (Lc + (Lc >> 4)) * 4;
 #define B200_FUSED_CASE(LL) case LL: { cudaError_t e; \
             if (DIF) { auto kf = k_ntt_invb<LL>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
                 if (pow_g) break; \
                 B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, scale); } \
-            else { auto kf = k_ntt_fwd1<LL>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
+            else if (lg_e == 2) { auto kf = k_ntt_fwd1<LL, 2>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
+                if (scale) break; \
+                B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, pow_g, lg_m, lg_rows); } \
+            else { auto kf = k_ntt_fwd1<LL, 0>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
                 if (scale) break; \
                 B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, pow_g, lg_m, lg_rows); } \
             return cudaGetLastError(); }
