@@ -31,6 +31,7 @@ extern "C" {
     pub fn b200_batch_expand_ntt(d_out: *mut u32, d_in: *const u32, lg_n: u32, lg_blowup: u32, count: u32, stream: *mut c_void) -> *const c_char;
     pub fn b200_batch_zk_shift(d_io: *mut u32, lg_n: u32, count: u32, stream: *mut c_void) -> *const c_char;
     pub fn b200_batch_bit_reverse(d_io: *mut u32, lg_n: u32, count: u32, stream: *mut c_void) -> *const c_char;
+    pub fn b200_batch_intt_zk_shift(d_io: *mut u32, lg_n: u32, count: u32, stream: *mut c_void) -> *const c_char;
 
     // kernel 2: Poseidon2 (sppark_poseidon2_rows / _fold)
     pub fn b200_poseidon2_rows(d_out: *mut u32, d_matrix: *const u32, rows: u32, cols: u32, stream: *mut c_void) -> *const c_char;

@@ -42,6 +42,9 @@ const char* b200_batch_expand_ntt(uint32_t* d_out, const uint32_t* d_in, uint32_
 const char* b200_batch_zk_shift(uint32_t* d_io, uint32_t lg_n, uint32_t count, void* stream) {
     TABLES(); RET(launch_zk_shift(T, d_io, lg_n, count, (cudaStream_t)stream));
 }
+const char* b200_batch_intt_zk_shift(uint32_t* d_io, uint32_t lg_n, uint32_t count, void* stream) {
+    TABLES(); RET(launch_batch_intt_shift(T, d_io, lg_n, count, (cudaStream_t)stream));
+}
 const char* b200_batch_bit_reverse(uint32_t* d_io, uint32_t lg_n, uint32_t count, void* stream) {
     RET(launch_bit_reverse(d_io, lg_n, count, (cudaStream_t)stream));
 }

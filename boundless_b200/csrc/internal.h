@@ -60,6 +60,8 @@ cudaError_t launch_batch_expand_ntt(const DeviceTables* T, uint32_t* d_out, cons
 // K2: coefficient of x^d *= 3^d (slot j holds degree bitrev(j))
 cudaError_t launch_zk_shift(const DeviceTables* T, uint32_t* d_io, uint32_t lg_n, uint32_t count, cudaStream_t s);
 cudaError_t launch_bit_reverse(uint32_t* d_io, uint32_t lg_n, uint32_t count, cudaStream_t s);
+// K1 + K2 fused (iNTT whose last pass applies the coset shift)
+cudaError_t launch_batch_intt_shift(const DeviceTables* T, uint32_t* d_io, uint32_t lg_n, uint32_t count, cudaStream_t s);
 
 // ---- Poseidon2 / Merkle / transcript (hash.cu) -------------------------------------------------------
 // K4: leaf j = sponge(matrix[c*col_stride + j], c < cols); out = rows x 8 words

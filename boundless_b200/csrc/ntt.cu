@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(256) k_ntt_fwd1(uint32_t* out, const uint32_t*
 template <int LOGLC>
 __global__ void __launch_bounds__(256) k_ntt_invb(uint32_t* out, const uint32_t* in, uint32_t rows_per_cta, uint32_t lg_rpp, uint32_t total_rows,
                                                   size_t in_poly_stride, size_t out_poly_stride, const uint32_t* __restrict__ tw_g,
-                                                  uint32_t scale) {
+                                                  uint32_t scale, const uint32_t* __restrict__ p3lo, const uint32_t* __restrict__ p3hi) {
     extern __shared__ uint32_t smem[];
     constexpr uint32_t Lc = 1u << LOGLC, rowpad = Lc + (Lc >> 4);
     constexpr int REM = LOGLC - 4;                   // levels after the first radix-16 stage
@@ -732,7 +732,13 @@ __global__ void __launch_bounds__(256) k_ntt_invb(uint32_t* out, const uint32_t*
             [&](uint32_t base, const uint32_t (&x)[1 << KF]) {
                 uint32_t v[1 << KF];
 #pragma unroll
-                for (int j = 0; j < (1 << KF); j++) v[j] = scale ? fp_mul(x[j], scale) : x[j];
+                for (int j = 0; j < (1 << KF); j++) {
+                    v[j] = scale ? fp_mul(x[j], scale) : x[j];
+                    if (p3lo) {   // fused zk_shift (K2): slot holds degree d = bitrev(row) + rows_per_poly * bitrev(pos); multiply by 3^d
+                        const uint32_t d = bitrev(R & rpp_mask, lg_rpp) + (bitrev(base + j, LOGLC) << lg_rpp);
+                        v[j] = fp_mul(v[j], fp_mul(__ldg(p3lo + (d & 4095)), __ldg(p3hi + (d >> 12))));
+                    }
+                }
                 if constexpr (KF == 1) *reinterpret_cast<uint2*>(orow + base) = make_uint2(v[0], v[1]);
                 else {
 #pragma unroll
@@ -817,7 +823,8 @@ static cudaError_t run_strided(const DeviceTables* T, uint32_t* d, uint32_t logL
 template <bool DIF>
 static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32_t* in, uint32_t logLc, uint32_t lg_e, uint32_t rows_per_poly,
                               uint32_t count, size_t in_stride, size_t out_stride, const uint32_t* pow_g, uint32_t lg_m,
-                              uint32_t lg_rows, uint32_t scale, cudaStream_t s) {
+                              uint32_t lg_rows, uint32_t scale, cudaStream_t s, const uint32_t* p3lo = nullptr, const uint32_t* p3hi = nullptr,
+                              bool* shift_done = nullptr) {
     uint32_t rpc = logLc >= 12 ? 1 : (1u << (12 - logLc));
     const uint64_t total_rows = (uint64_t)rows_per_poly * count;
     if (rpc > total_rows) rpc = (uint32_t)total_rows;
@@ -833,7 +840,8 @@ static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32
 #define B200_FUSED_CASE(LL) case LL: { cudaError_t e; \
             if (DIF) { auto kf = k_ntt_invb<LL>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
                 if (pow_g) break; \
-                B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, scale); } \
+                B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, scale, p3lo, p3hi); \
+                if (shift_done) *shift_done = p3lo != nullptr; } \
             else if (lg_e == 2) { auto kf = k_ntt_fwd1<LL, 2>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
                 if (scale) break; \
                 B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, pow_g, lg_m, lg_rows); } \
@@ -875,6 +883,27 @@ cudaError_t launch_batch_intt(const DeviceTables* T, uint32_t* d_io, uint32_t lg
     if (e != cudaSuccess) return e;
     // pass B: DIF over each contiguous row of N2
     return run_contig<true>(T, d_io, d_io, n2, 0, 1u << n1, count, N, N, nullptr, 0, 0, 0, s);
+}
+
+// K1 + K2 in one go: iNTT whose last pass multiplies the coefficient of x^d by 3^d (falls back to two launches when the
+// fused kernel does not cover the shape).
+cudaError_t launch_batch_intt_shift(const DeviceTables* T, uint32_t* d_io, uint32_t lg_n, uint32_t count, cudaStream_t s) {
+    if (count == 0) return cudaSuccess;
+    if (lg_n == 0 || lg_n > MAX_LG) return lg_n == 0 ? cudaSuccess : cudaErrorInvalidValue;     // 3^0 = 1 for size-1 polynomials
+    const size_t N = (size_t)1 << lg_n;
+    bool done = false;
+    cudaError_t e;
+    if (lg_n <= 12) {
+        const uint32_t scale = h_inv(h_to_mont((uint32_t)N));
+        e = run_contig<true>(T, d_io, d_io, lg_n, 0, 1, count, N, N, nullptr, 0, 0, scale, s, T->p3lo, T->p3hi, &done);
+    } else {
+        const uint32_t n1 = split_n1(lg_n), n2 = lg_n - n1;
+        e = run_strided<true>(T, d_io, n1, 1u << n2, 1u << n2, count, N, T->pow_inv[lg_n], lg_n, s);
+        if (e != cudaSuccess) return e;
+        e = run_contig<true>(T, d_io, d_io, n2, 0, 1u << n1, count, N, N, nullptr, 0, 0, 0, s, T->p3lo, T->p3hi, &done);
+    }
+    if (e != cudaSuccess) return e;
+    return done ? cudaSuccess : launch_zk_shift(T, d_io, lg_n, count, s);
 }
 
 cudaError_t launch_batch_expand_ntt(const DeviceTables* T, uint32_t* d_out, const uint32_t* d_in, uint32_t lg_n, uint32_t lg_e,

@@ -159,8 +159,7 @@ static const char* commit_group(b200_prover* p, Slot& s, uint32_t* coeffs, uint3
     cudaStream_t st = s.stream;
     const uint32_t D = 4u << po2;
     if (interp_shift) {
-        KL(launch_batch_intt(p->T, coeffs, po2, cols, st));             // K1
-        KL(launch_zk_shift(p->T, coeffs, po2, cols, st));               // K2
+        KL(launch_batch_intt_shift(p->T, coeffs, po2, cols, st));      // K1 + K2 (coset shift fused into the last iNTT pass)
     }
     KL(launch_batch_expand_ntt(p->T, evals, coeffs, po2, INV_RATE_LG, cols, st));   // K3
     KL(launch_poseidon2_rows(nodes + (size_t)D * 8, evals, D, cols, D, st));         // K4

@@ -38,6 +38,7 @@ SYMBOLS = {
     "b200_batch_expand_ntt": (_cp, [_vp, _vp, _u32, _u32, _u32, _vp]),
     "b200_batch_zk_shift": (_cp, [_vp, _u32, _u32, _vp]),
     "b200_batch_bit_reverse": (_cp, [_vp, _u32, _u32, _vp]),
+    "b200_batch_intt_zk_shift": (_cp, [_vp, _u32, _u32, _vp]),
     "b200_poseidon2_rows": (_cp, [_vp, _vp, _u32, _u32, _vp]),
     "b200_poseidon2_fold": (_cp, [_vp, _vp, _u32, _vp]),
     "b200_merkle_tree": (_cp, [_vp, _vp, _u32, _u32, _vp]),

@@ -47,6 +47,8 @@ const char* b200_batch_expand_ntt(uint32_t* d_out, const uint32_t* d_in, uint32_
 /* K2: coefficient of x^d *= 3^d (slot j holds degree bitrev(j)) */
 const char* b200_batch_zk_shift(uint32_t* d_io, uint32_t lg_n, uint32_t count, void* stream);
 const char* b200_batch_bit_reverse(uint32_t* d_io, uint32_t lg_n, uint32_t count, void* stream);
+/* K1 + K2 fused: b200_batch_intt followed by b200_batch_zk_shift in one pass over the data (what commit_group uses) */
+const char* b200_batch_intt_zk_shift(uint32_t* d_io, uint32_t lg_n, uint32_t count, void* stream);
 
 /* ---- kernel 2: Poseidon2 (replaces sppark_poseidon2_rows / sppark_poseidon2_fold) ---------------------------- */
 /* K4: d_out[rows][8]; leaf j = sponge over d_matrix[c*rows + j], c < cols */

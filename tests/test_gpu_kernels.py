@@ -57,7 +57,13 @@ def test_batch_intt_and_shift(gpu, b200lib, oracle, lg_n, count):
     assert np.array_equal(host(d), ref)
     ck(b200lib.b200_batch_zk_shift(ptr(d), lg_n, count, None))
     torch.cuda.synchronize()
-    assert np.array_equal(host(d), oracle.batch_zk_shift(ref, lg_n, count))
+    shifted = oracle.batch_zk_shift(ref, lg_n, count)
+    assert np.array_equal(host(d), shifted)
+    # the fused K1+K2 entry point gives the same coefficients in one pass
+    d2 = dev(torch, a)
+    ck(b200lib.b200_batch_intt_zk_shift(ptr(d2), lg_n, count, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(host(d2), shifted)
 
 
 @pytest.mark.parametrize("lg_n,count", [(1, 2), (5, 3), (10, 4), (12, 5), (13, 2), (14, 3), (16, 4), (17, 2), (20, 2), (22, 1)])
