@@ -26,14 +26,15 @@ struct DeviceTables {
     int device;
     int sm_count;
     // stage twiddles, compact per-level layout: tw[2^(l-1) + i] = w_{2^l}^i, i < 2^(l-1), l <= 12
-    uint32_t* tw_fwd;      // 4096 entries
-    uint32_t* tw_inv;      // 4096 entries
+    // every twiddle table holds Shoup pairs {w, floor(w * 2^32 / p)} with w the PLAIN value (csrc/ntt.cu mul_tw)
+    uint2* tw_fwd;         // 8192 pairs
+    uint2* tw_inv;         // 8192 pairs
     // six-step inter-pass twiddle decomposition for transform size 2^m:  w_{2^m}^e = lo[e & (2^h-1)] * hi[e >> h], h = ceil(m/2)
-    uint32_t* pow_fwd[MAX_LG + 1];      // lo (2^h) followed by hi (2^(m-h))
-    uint32_t* pow_inv[MAX_LG + 1];      // inverse roots; hi table pre-scaled by 2^-m (iNTT normalisation)
+    uint2* pow_fwd[MAX_LG + 1];      // lo (2^h) followed by hi (2^(m-h))
+    uint2* pow_inv[MAX_LG + 1];      // inverse roots; hi table pre-scaled by 2^-m (iNTT normalisation)
     // zk_shift: 3^d = p3lo[d & 4095] * p3hi[d >> 12]
-    uint32_t* p3lo;
-    uint32_t* p3hi;
+    uint2* p3lo;
+    uint2* p3hi;
     uint32_t rou_fwd[28], rou_rev[28];  // host copies, Montgomery
 };
 const DeviceTables* get_tables(int device);   // lazily built, thread-safe; nullptr + error string on failure

@@ -45,10 +45,22 @@ struct AddrContig {
     __device__ __forceinline__ static constexpr uint32_t off(uint32_t d) { return d + (d >> 4); }
 };
 
+// Twiddles are table CONSTANTS, so they are stored as Shoup pairs {w, floor(w * 2^32 / p)} with w the plain (non-Montgomery)
+// value: x~ * w mod p keeps x~ in Montgomery form and costs IMAD.HI + 2 IMAD (8 multiplier-pipe cycles) instead of
+// IMAD.WIDE + IMAD + IMAD.HI (10).  x may be any u32, the result is canonical.
+typedef uint2 tw_t;
+__device__ __forceinline__ uint32_t mul_tw(uint32_t x, const tw_t w) {
+    const uint32_t q = __umulhi(x, w.y);
+    const uint32_t r = x * w.x - q * P;          // in [0, 2p)
+    return addmin(r, 0u - P, r);
+}
+// v * lo * hi with both factors from the two-table decomposition w^e = lo[e & mask] * hi[e >> h]
+__device__ __forceinline__ uint32_t pow_apply(uint32_t v, const tw_t lo, const tw_t hi) { return mul_tw(mul_tw(v, lo), hi); }
+
 // One radix-2^K register stage: gathers the 2^K elements base + j*q of the block of size 2^lb that contains them,
 // runs K butterfly levels in registers and scatters them back.  tw is the compact table tw[2^(l-1)+i] = w_{2^l}^i.
 template <int K, bool DIF, typename ADDR>
-__device__ __forceinline__ void ntt_stage(uint32_t* s, const uint32_t* __restrict__ tw, uint32_t lb, uint32_t gidx, ADDR addr) {
+__device__ __forceinline__ void ntt_stage(uint32_t* s, const tw_t* __restrict__ tw, uint32_t lb, uint32_t gidx, ADDR addr) {
     constexpr int R = 1 << K;
     const uint32_t q = (1u << lb) >> K;
     const uint32_t b = gidx >> (lb - K), o = gidx & (q - 1);
@@ -64,13 +76,13 @@ __device__ __forceinline__ void ntt_stage(uint32_t* s, const uint32_t* __restric
 #pragma unroll
         for (int j = 0; j < R; j++) {
             if ((j & half) == 0) {
-                const uint32_t w = tw[twbase + (j & (half - 1)) * q];
+                const tw_t w = tw[twbase + (j & (half - 1)) * q];
                 const uint32_t a = x[j], bb = x[j + half];
                 if (DIF) {
                     x[j] = fp_add(a, bb);
-                    x[j + half] = fp_mul(fp_sub(a, bb), w);
+                    x[j + half] = mul_tw(fp_sub(a, bb), w);
                 } else {
-                    const uint32_t t = fp_mul(bb, w);
+                    const uint32_t t = mul_tw(bb, w);
                     x[j] = fp_add(a, t);
                     x[j + half] = fp_sub(a, t);
                 }
@@ -82,7 +94,7 @@ __device__ __forceinline__ void ntt_stage(uint32_t* s, const uint32_t* __restric
 }
 
 template <bool DIF, typename ADDR>
-__device__ __forceinline__ void ntt_stage_k(int K, uint32_t* s, const uint32_t* tw, uint32_t lb, uint32_t gidx, ADDR addr) {
+__device__ __forceinline__ void ntt_stage_k(int K, uint32_t* s, const tw_t* tw, uint32_t lb, uint32_t gidx, ADDR addr) {
     switch (K) {
         case 4: ntt_stage<4, DIF>(s, tw, lb, gidx, addr); break;
         case 3: ntt_stage<3, DIF>(s, tw, lb, gidx, addr); break;
@@ -91,9 +103,9 @@ __device__ __forceinline__ void ntt_stage_k(int K, uint32_t* s, const uint32_t* 
     }
 }
 
-struct PowTab {          // w^e = lo[e & mask] * hi[e >> h]
-    const uint32_t* lo; const uint32_t* hi; uint32_t h, mask;
-    __device__ __forceinline__ uint32_t operator()(uint32_t e) const { return fp_mul(lo[e & mask], hi[e >> h]); }
+struct PowTab {
+    const tw_t* lo; const tw_t* hi; uint32_t h, mask;
+    __device__ __forceinline__ uint32_t apply(uint32_t v, uint32_t e) const { return pow_apply(v, lo[e & mask], hi[e >> h]); }
 };
 
 // ---- strided pass: tile [L][TW], FFT along rows -------------------------------------------------------
@@ -101,13 +113,13 @@ struct PowTab {          // w^e = lo[e & mask] * hi[e >> h]
 template <bool DIF>
 __global__ void __launch_bounds__(512) k_ntt_strided(uint32_t* __restrict__ data, uint32_t logL, uint32_t lgTW, uint32_t row_stride,
                                                      uint32_t tiles_per_poly, size_t poly_stride,
-                                                     const uint32_t* __restrict__ tw_g, const uint32_t* __restrict__ pow_g,
+                                                     const tw_t* __restrict__ tw_g, const tw_t* __restrict__ pow_g,
                                                      uint32_t lg_m) {
     extern __shared__ uint32_t smem[];
     const uint32_t L = 1u << logL, TW = 1u << lgTW;
     uint32_t* tile = smem;                  // L * TW
-    uint32_t* tw = tile + (L << lgTW);      // L
-    uint32_t* pw = tw + L;                  // 2^h + 2^(m-h) when pow_g
+    tw_t* tw = reinterpret_cast<tw_t*>(tile + (L << lgTW));      // L pairs
+    tw_t* pw = tw + L;                      // 2^h + 2^(m-h) pairs when pow_g
     const uint32_t tid = threadIdx.x, nth = blockDim.x;
     const uint32_t poly = blockIdx.x / tiles_per_poly, tcol = blockIdx.x % tiles_per_poly;
     uint32_t* g = data + (size_t)poly * poly_stride + ((size_t)tcol << lgTW);
@@ -144,7 +156,7 @@ __global__ void __launch_bounds__(512) k_ntt_strided(uint32_t* __restrict__ data
         for (uint32_t i = tid; i < (L << lgTW); i += nth) {
             const uint32_t r = i >> lgTW, c = (tcol << lgTW) + (i & (TW - 1));
             const uint32_t e = (c * bitrev(r, logL)) & mmask;
-            g[(size_t)r * row_stride + (i & (TW - 1))] = fp_mul(tile[i], pt(e));
+            g[(size_t)r * row_stride + (i & (TW - 1))] = pt.apply(tile[i], e);
         }
     } else {
         for (uint32_t i = tid; i < (L << lgTW); i += nth) g[(size_t)(i >> lgTW) * row_stride + (i & (TW - 1))] = tile[i];
@@ -157,14 +169,14 @@ template <bool DIF>
 __global__ void __launch_bounds__(256) k_ntt_contig(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, uint32_t logLc,
                                                     uint32_t lg_e, uint32_t rows_per_cta, uint32_t rows_per_poly, uint32_t total_rows,
                                                     size_t in_poly_stride, size_t out_poly_stride,
-                                                    const uint32_t* __restrict__ tw_g, const uint32_t* __restrict__ pow_g,
+                                                    const tw_t* __restrict__ tw_g, const tw_t* __restrict__ pow_g,
                                                     uint32_t lg_m, uint32_t lg_rows, uint32_t scale) {
     extern __shared__ uint32_t smem[];
     const uint32_t Lc = 1u << logLc, Lin = Lc >> lg_e;
     const uint32_t rowpad = Lc + (Lc >> 4);
     uint32_t* tile = smem;                              // rows_per_cta * rowpad
-    uint32_t* tw = tile + rows_per_cta * rowpad;        // Lc
-    uint32_t* pw = tw + Lc;
+    tw_t* tw = reinterpret_cast<tw_t*>(tile + ((rows_per_cta * rowpad + 1) & ~1u));        // Lc pairs
+    tw_t* pw = tw + Lc;
     const uint32_t tid = threadIdx.x, nth = blockDim.x;
     const uint32_t row0 = blockIdx.x * rows_per_cta;
 
@@ -210,7 +222,7 @@ __global__ void __launch_bounds__(256) k_ntt_contig(uint32_t* __restrict__ out, 
         if (R < total_rows) {
             const uint32_t poly = R / rows_per_poly, rho = R - poly * rows_per_poly;
             uint32_t v = tile[AddrContig{rr * rowpad}(k)];
-            if (pow_g) v = fp_mul(v, pt((k * bitrev(rho, lg_rows)) & mmask));
+            if (pow_g) v = pt.apply(v, (k * bitrev(rho, lg_rows)) & mmask);
             else if (scale) v = fp_mul(v, scale);
             out[(size_t)poly * out_poly_stride + (size_t)rho * Lc + k] = v;
         }
@@ -226,7 +238,7 @@ template <typename A> __device__ __forceinline__ uint32_t addr_base(const A& a, 
 __device__ __forceinline__ uint32_t addr_base(const AddrContig& a, uint32_t pos) { return a.base_of(pos); }
 
 template <int K, int LB, bool DIF, bool TWS = false, typename ADDR>
-__device__ __forceinline__ void ntt_stage_c(uint32_t* s, const uint32_t* __restrict__ tw, uint32_t gidx, ADDR addr) {
+__device__ __forceinline__ void ntt_stage_c(uint32_t* s, const tw_t* __restrict__ tw, uint32_t gidx, ADDR addr) {
     constexpr int R = 1 << K;
     constexpr uint32_t q = (1u << LB) >> K;
     const uint32_t b = gidx >> (LB - K), o = gidx & (q - 1);
@@ -236,7 +248,7 @@ __device__ __forceinline__ void ntt_stage_c(uint32_t* s, const uint32_t* __restr
     const uint32_t a0 = addr_base(addr, base);
 #pragma unroll
     for (int j = 0; j < R; j++) x[j] = s[a0 + addr.off(j * q)];
-    const uint32_t* twp = tw + o;
+    const tw_t* twp = tw + o;
 #pragma unroll
     for (int ll = 0; ll < K; ll++) {
         const int l = DIF ? ll : (K - 1 - ll);
@@ -244,14 +256,14 @@ __device__ __forceinline__ void ntt_stage_c(uint32_t* s, const uint32_t* __restr
 #pragma unroll
         for (int j = 0; j < R; j++) {
             if ((j & half) == 0) {
-                const uint32_t* wp = twp + ((1u << LB) >> (l + 1)) + (j & (half - 1)) * q;
-                const uint32_t w = TWS ? *wp : __ldg(wp);      // TWS: table staged in shared memory by TMA
+                const tw_t* wp = twp + ((1u << LB) >> (l + 1)) + (j & (half - 1)) * q;
+                const tw_t w = TWS ? *wp : __ldg(wp);      // TWS: table staged in shared memory by TMA
                 const uint32_t a = x[j], bb = x[j + half];
                 if (DIF) {
                     x[j] = fp_add(a, bb);
-                    x[j + half] = fp_mul(fp_sub(a, bb), w);
+                    x[j + half] = mul_tw(fp_sub(a, bb), w);
                 } else {
-                    const uint32_t t = fp_mul(bb, w);
+                    const uint32_t t = mul_tw(bb, w);
                     x[j] = fp_add(a, t);
                     x[j + half] = fp_sub(a, t);
                 }
@@ -266,7 +278,7 @@ __device__ __forceinline__ void ntt_stage_c(uint32_t* s, const uint32_t* __restr
 template <int LOGL, int LOW, bool DIF, int DONE = 0, bool TWS = false>
 struct NttStages {
     template <typename MK>
-    static __device__ __forceinline__ void run(uint32_t* s, const uint32_t* tw, uint32_t tid, uint32_t nth, uint32_t nbatch_shift, MK mk) {
+    static __device__ __forceinline__ void run(uint32_t* s, const tw_t* tw, uint32_t tid, uint32_t nth, uint32_t nbatch_shift, MK mk) {
         constexpr int REM = LOGL - LOW - DONE;
         if constexpr (REM > 0) {
             // DIT takes the remainder stage first (next to the expand), DIF takes it last
@@ -297,8 +309,8 @@ struct MkStrided {      // work item w -> (group index, column t)
 };
 template <int LOGL, bool DIF>
 __global__ void __launch_bounds__(512) k_ntt_strided_c(uint32_t* __restrict__ data, uint32_t lgTW, uint32_t row_stride, uint32_t tiles_per_poly,
-                                                       size_t poly_stride, const uint32_t* __restrict__ tw_g,
-                                                       const uint32_t* __restrict__ pow_g, uint32_t lg_m) {
+                                                       size_t poly_stride, const tw_t* __restrict__ tw_g,
+                                                       const tw_t* __restrict__ pow_g, uint32_t lg_m) {
     extern __shared__ uint32_t smem[];
     constexpr uint32_t L = 1u << LOGL;
     const uint32_t TW = 1u << lgTW;
@@ -325,7 +337,7 @@ __global__ void __launch_bounds__(512) k_ntt_strided_c(uint32_t* __restrict__ da
         const uint32_t* tp = tile + (r0 << lgTW) + c;
         for (uint32_t r = r0; r < L; r += rstep) {
             const uint32_t e = (col * bitrev(r, LOGL)) & mmask;
-            *gp = fp_mul(*tp, fp_mul(__ldg(pt.lo + (e & pt.mask)), __ldg(pt.hi + (e >> h))));
+            *gp = pow_apply(*tp, __ldg(pt.lo + (e & pt.mask)), __ldg(pt.hi + (e >> h)));
             gp += gstep; tp += rstep << lgTW;
         }
     } else {
@@ -365,19 +377,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
 
 template <int LOGL, bool DIF>
 __global__ void __launch_bounds__(512) k_ntt_strided_p(uint32_t* __restrict__ data, uint32_t row_stride, uint32_t tiles_per_poly,
-                                                       uint32_t num_tiles, size_t poly_stride, const uint32_t* __restrict__ tw_g,
-                                                       const uint32_t* __restrict__ pow_g, uint32_t lg_m) {
+                                                       uint32_t num_tiles, size_t poly_stride, const tw_t* __restrict__ tw_g,
+                                                       const tw_t* __restrict__ pow_g, uint32_t lg_m) {
     extern __shared__ __align__(16) uint32_t smem[];
     constexpr uint32_t L = 1u << LOGL, TILE = (L + (L >> 4)) * 8;
     const uint32_t tid = threadIdx.x, nth = blockDim.x;
     const uint32_t h = (lg_m + 1) / 2, lmask = (1u << h) - 1, mmask = (1u << lg_m) - 1;
-    const uint32_t* plo = pow_g; const uint32_t* phi = pow_g + (1u << h);
+    const tw_t* plo = pow_g; const tw_t* phi = pow_g + (1u << h);
     // stage twiddles (L words) live behind the two tile buffers; one TMA bulk copy per CTA, awaited before the first stage
-    uint32_t* tw_s = smem + 2 * TILE;
+    tw_t* tw_s = reinterpret_cast<tw_t*>(smem + 2 * TILE);
     __shared__ __align__(8) uint64_t tw_bar;
     if (tid == 0) mbar_init(&tw_bar, 1);
     __syncthreads();
-    if (tid == 0) tma_load_1d(tw_s, tw_g, L * 4, &tw_bar);
+    if (tid == 0) tma_load_1d(tw_s, tw_g, L * 8, &tw_bar);
     auto tile_ptr = [&](uint32_t tile) { return data + (size_t)(tile / tiles_per_poly) * poly_stride + (size_t)(tile % tiles_per_poly) * 8; };
     auto issue_load = [&](uint32_t tile, uint32_t* buf) {
         const uint32_t* g = tile_ptr(tile);
@@ -403,10 +415,10 @@ __global__ void __launch_bounds__(512) k_ntt_strided_p(uint32_t* __restrict__ da
             if (pow_g) {
                 const uint32_t d1 = bitrev(r, LOGL);
                 uint32_t e = ((col0 + c4) * d1) & mmask;
-                v.x = fp_mul(v.x, fp_mul(__ldg(plo + (e & lmask)), __ldg(phi + (e >> h)))); e = (e + d1) & mmask;
-                v.y = fp_mul(v.y, fp_mul(__ldg(plo + (e & lmask)), __ldg(phi + (e >> h)))); e = (e + d1) & mmask;
-                v.z = fp_mul(v.z, fp_mul(__ldg(plo + (e & lmask)), __ldg(phi + (e >> h)))); e = (e + d1) & mmask;
-                v.w = fp_mul(v.w, fp_mul(__ldg(plo + (e & lmask)), __ldg(phi + (e >> h))));
+                v.x = pow_apply(v.x, __ldg(plo + (e & lmask)), __ldg(phi + (e >> h))); e = (e + d1) & mmask;
+                v.y = pow_apply(v.y, __ldg(plo + (e & lmask)), __ldg(phi + (e >> h))); e = (e + d1) & mmask;
+                v.z = pow_apply(v.z, __ldg(plo + (e & lmask)), __ldg(phi + (e >> h))); e = (e + d1) & mmask;
+                v.w = pow_apply(v.w, __ldg(plo + (e & lmask)), __ldg(phi + (e >> h)));
             }
             *reinterpret_cast<uint4*>(g + (size_t)r * row_stride + c4) = v;
         }
@@ -419,7 +431,7 @@ __global__ void __launch_bounds__(512) k_ntt_strided_p(uint32_t* __restrict__ da
 template <int LOGLC, int LGE, bool DIF>
 __global__ void __launch_bounds__(256) k_ntt_contig_c(uint32_t* out, const uint32_t* in, uint32_t rows_per_cta, uint32_t lg_rpp,
                                                       uint32_t total_rows, size_t in_poly_stride, size_t out_poly_stride,
-                                                      const uint32_t* __restrict__ tw_g, const uint32_t* __restrict__ pow_g,
+                                                      const tw_t* __restrict__ tw_g, const tw_t* __restrict__ pow_g,
                                                       uint32_t lg_m, uint32_t lg_rows, uint32_t scale) {
     extern __shared__ uint32_t smem[];
     constexpr uint32_t Lc = 1u << LOGLC, Lin = Lc >> LGE, rowpad = Lc + (Lc >> 4);
@@ -458,7 +470,7 @@ __global__ void __launch_bounds__(256) k_ntt_contig_c(uint32_t* out, const uint3
         if constexpr (K4 > 0) { for (uint32_t w = tid; w < rows_per_cta << (LOGLC - K4); w += nth) ntt_stage_c<K4, LGE + K1 + K2 + K3 + K4, false>(tile, tw_g, w & ((1u << (LOGLC - K4)) - 1), AddrContig{(w >> (LOGLC - K4)) * rowpad}); __syncthreads(); }
     }
     const uint32_t h = (lg_m + 1) / 2;
-    const uint32_t* plo = pow_g; const uint32_t* phi = pow_g + (1u << h);
+    const tw_t* plo = pow_g; const tw_t* phi = pow_g + (1u << h);
     const uint32_t lmask = (1u << h) - 1, mmask = (1u << lg_m) - 1;
     for (uint32_t rr = 0; rr < rows_per_cta; rr++) {
         const uint32_t R = row0 + rr;
@@ -473,7 +485,7 @@ __global__ void __launch_bounds__(256) k_ntt_contig_c(uint32_t* out, const uint3
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 v[i] = trow[ph + i];
-                if (pow_g) { const uint32_t e = ((k + i) * d1) & mmask; v[i] = fp_mul(v[i], fp_mul(__ldg(plo + (e & lmask)), __ldg(phi + (e >> h)))); }
+                if (pow_g) { const uint32_t e = ((k + i) * d1) & mmask; v[i] = pow_apply(v[i], __ldg(plo + (e & lmask)), __ldg(phi + (e >> h))); }
                 else if (scale) v[i] = fp_mul(v[i], scale);
             }
             dst[k4] = make_uint4(v[0], v[1], v[2], v[3]);
@@ -489,7 +501,7 @@ __global__ void __launch_bounds__(256) k_ntt_contig_c(uint32_t* out, const uint3
 // per middle stage instead of load + every stage + store.
 // =========================================================================================================
 template <int K, int LB, bool DIF, bool TWS = false, typename LD, typename ST>
-__device__ __forceinline__ void ntt_stage_io(const uint32_t* __restrict__ tw, uint32_t gidx, LD ld, ST st) {
+__device__ __forceinline__ void ntt_stage_io(const tw_t* __restrict__ tw, uint32_t gidx, LD ld, ST st) {
     constexpr int R = 1 << K;
     constexpr uint32_t q = (1u << LB) >> K;
     const uint32_t b = gidx >> (LB - K), o = gidx & (q - 1);
@@ -497,7 +509,7 @@ __device__ __forceinline__ void ntt_stage_io(const uint32_t* __restrict__ tw, ui
     uint32_t x[R];
 #pragma unroll
     for (int j = 0; j < R; j++) x[j] = ld(base, (uint32_t)(j * q));
-    const uint32_t* twp = tw + o;
+    const tw_t* twp = tw + o;
 #pragma unroll
     for (int ll = 0; ll < K; ll++) {
         const int l = DIF ? ll : (K - 1 - ll);
@@ -505,11 +517,11 @@ __device__ __forceinline__ void ntt_stage_io(const uint32_t* __restrict__ tw, ui
 #pragma unroll
         for (int j = 0; j < R; j++) {
             if ((j & half) == 0) {
-                const uint32_t* wp = twp + ((1u << LB) >> (l + 1)) + (j & (half - 1)) * q;
-                const uint32_t w = TWS ? *wp : __ldg(wp);
+                const tw_t* wp = twp + ((1u << LB) >> (l + 1)) + (j & (half - 1)) * q;
+                const tw_t w = TWS ? *wp : __ldg(wp);
                 const uint32_t a = x[j], bb = x[j + half];
-                if (DIF) { x[j] = fp_add(a, bb); x[j + half] = fp_mul(fp_sub(a, bb), w); }
-                else { const uint32_t t = fp_mul(bb, w); x[j] = fp_add(a, t); x[j + half] = fp_sub(a, t); }
+                if (DIF) { x[j] = fp_add(a, bb); x[j + half] = mul_tw(fp_sub(a, bb), w); }
+                else { const uint32_t t = mul_tw(bb, w); x[j] = fp_add(a, t); x[j + half] = fp_sub(a, t); }
             }
         }
     }
@@ -521,20 +533,20 @@ __device__ __forceinline__ void ntt_stage_io(const uint32_t* __restrict__ tw, ui
 // makes one shared-memory round trip less and needs one barrier less than k_ntt_strided_p.
 template <int LOGL, bool DIF>
 __global__ void __launch_bounds__(512) k_ntt_strided_pf(uint32_t* __restrict__ data, uint32_t row_stride, uint32_t tiles_per_poly,
-                                                        uint32_t num_tiles, size_t poly_stride, const uint32_t* __restrict__ tw_g,
-                                                        const uint32_t* __restrict__ pow_g, uint32_t lg_m) {
+                                                        uint32_t num_tiles, size_t poly_stride, const tw_t* __restrict__ tw_g,
+                                                        const tw_t* __restrict__ pow_g, uint32_t lg_m) {
     extern __shared__ __align__(16) uint32_t smem[];
     constexpr uint32_t L = 1u << LOGL, TILE = (L + (L >> 4)) * 8;
     constexpr int KF = (LOGL % 4) ? (LOGL % 4) : 4, NFULL = (LOGL - KF) / 4;
     static_assert(NFULL >= 1 && NFULL <= 2, "unsupported tile height");
     const uint32_t tid = threadIdx.x, nth = blockDim.x;
     const uint32_t h = (lg_m + 1) / 2, lmask = (1u << h) - 1, mmask = (1u << lg_m) - 1;
-    const uint32_t* plo = pow_g; const uint32_t* phi = pow_g + (1u << h);
-    uint32_t* tw_s = smem + 2 * TILE;
+    const tw_t* plo = pow_g; const tw_t* phi = pow_g + (1u << h);
+    tw_t* tw_s = reinterpret_cast<tw_t*>(smem + 2 * TILE);
     __shared__ __align__(8) uint64_t tw_bar;
     if (tid == 0) mbar_init(&tw_bar, 1);
     __syncthreads();
-    if (tid == 0) tma_load_1d(tw_s, tw_g, L * 4, &tw_bar);
+    if (tid == 0) tma_load_1d(tw_s, tw_g, L * 8, &tw_bar);
     auto issue_load = [&](uint32_t tile, uint32_t* buf) {
         const uint32_t* g = data + (size_t)(tile / tiles_per_poly) * poly_stride + (size_t)(tile % tiles_per_poly) * 8;
         for (uint32_t ch = tid; ch < 2 * L; ch += nth) { const uint32_t r = ch >> 1; cp_async16(buf + (r + (r >> 4)) * 8 + (ch & 1) * 4, g + (size_t)r * row_stride + (ch & 1) * 4); }
@@ -572,7 +584,7 @@ __global__ void __launch_bounds__(512) k_ntt_strided_pf(uint32_t* __restrict__ d
                     for (int j = 0; j < (1 << KF); j++) {
                         const uint32_t row = base + j * QF;
                         uint32_t v = x[j];
-                        if (pow_g) { const uint32_t e = ((col0 + t) * bitrev(row, LOGL)) & mmask; v = fp_mul(v, fp_mul(__ldg(plo + (e & lmask)), __ldg(phi + (e >> h)))); }
+                        if (pow_g) { const uint32_t e = ((col0 + t) * bitrev(row, LOGL)) & mmask; v = pow_apply(v, __ldg(plo + (e & lmask)), __ldg(phi + (e >> h))); }
                         g[(size_t)row * row_stride + t] = v;
                     }
                 });
@@ -587,7 +599,7 @@ __global__ void __launch_bounds__(512) k_ntt_strided_pf(uint32_t* __restrict__ d
 template <int LOGLC, int LGE>
 __global__ void __launch_bounds__(256) k_ntt_fwd1(uint32_t* out, const uint32_t* in, uint32_t rows_per_cta, uint32_t lg_rpp,
                                                   uint32_t total_rows, size_t in_poly_stride, size_t out_poly_stride,
-                                                  const uint32_t* __restrict__ tw_g, const uint32_t* __restrict__ pow_g, uint32_t lg_m,
+                                                  const tw_t* __restrict__ tw_g, const tw_t* __restrict__ pow_g, uint32_t lg_m,
                                                   uint32_t lg_rows) {
     extern __shared__ uint32_t smem[];
     static_assert(LGE == 0 || LGE == 2, "blow-up 1 or 4");
@@ -613,8 +625,8 @@ __global__ void __launch_bounds__(256) k_ntt_fwd1(uint32_t* out, const uint32_t*
                                       });
         }
     } else {   // expand x4 + levels 3,4
-        const uint32_t w8_1 = __ldg(tw_g + 5), w8_2 = __ldg(tw_g + 6), w8_3 = __ldg(tw_g + 7);       // w_8^i  at tw[4+i]
-        uint32_t w16[8];
+        const tw_t w8_1 = __ldg(tw_g + 5), w8_2 = __ldg(tw_g + 6), w8_3 = __ldg(tw_g + 7);       // w_8^i  at tw[4+i]
+        tw_t w16[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) w16[i] = __ldg(tw_g + 8 + i);                                       // w_16^i at tw[8+i]
         for (uint32_t w = tid; w < nrows << (LOGLC - 4); w += nth) {
@@ -622,12 +634,12 @@ __global__ void __launch_bounds__(256) k_ntt_fwd1(uint32_t* out, const uint32_t*
             const uint4 c = *reinterpret_cast<const uint4*>(in + (size_t)(R >> lg_rpp) * in_poly_stride + (size_t)(R & rpp_mask) * Lin + 4 * t);
             uint32_t y[16];
             {   // level 3 on (c.x, c.y) -> y[0..7], on (c.z, c.w) -> y[8..15]
-                const uint32_t b1 = fp_mul(c.y, w8_1), b2 = fp_mul(c.y, w8_2), b3 = fp_mul(c.y, w8_3);
+                const uint32_t b1 = mul_tw(c.y, w8_1), b2 = mul_tw(c.y, w8_2), b3 = mul_tw(c.y, w8_3);
                 y[0] = fp_add(c.x, c.y); y[4] = fp_sub(c.x, c.y);
                 y[1] = fp_add(c.x, b1);  y[5] = fp_sub(c.x, b1);
                 y[2] = fp_add(c.x, b2);  y[6] = fp_sub(c.x, b2);
                 y[3] = fp_add(c.x, b3);  y[7] = fp_sub(c.x, b3);
-                const uint32_t d1 = fp_mul(c.w, w8_1), d2 = fp_mul(c.w, w8_2), d3 = fp_mul(c.w, w8_3);
+                const uint32_t d1 = mul_tw(c.w, w8_1), d2 = mul_tw(c.w, w8_2), d3 = mul_tw(c.w, w8_3);
                 y[8] = fp_add(c.z, c.w);  y[12] = fp_sub(c.z, c.w);
                 y[9] = fp_add(c.z, d1);   y[13] = fp_sub(c.z, d1);
                 y[10] = fp_add(c.z, d2);  y[14] = fp_sub(c.z, d2);
@@ -636,7 +648,7 @@ __global__ void __launch_bounds__(256) k_ntt_fwd1(uint32_t* out, const uint32_t*
             uint32_t* dst = tile + rr * rowpad + 17 * t;        // phys(16t + j) = 16t + j + t
 #pragma unroll
             for (int i = 0; i < 8; i++) {                        // level 4
-                const uint32_t bb = i == 0 ? y[8] : fp_mul(y[8 + i], w16[i]);
+                const uint32_t bb = i == 0 ? y[8] : mul_tw(y[8 + i], w16[i]);
                 dst[i] = fp_add(y[i], bb);
                 dst[8 + i] = fp_sub(y[i], bb);
             }
@@ -659,7 +671,7 @@ __global__ void __launch_bounds__(256) k_ntt_fwd1(uint32_t* out, const uint32_t*
     static_assert(NMID4 <= 1, "row too long for the fused kernel");
     // ---- last stage (levels LOGLC-3..LOGLC) straight to global, times the inter-pass twiddle ----
     const uint32_t h = (lg_m + 1) / 2, lmask = (1u << h) - 1, mmask = (1u << lg_m) - 1;
-    const uint32_t* plo = pow_g; const uint32_t* phi = pow_g + (1u << h);
+    const tw_t* plo = pow_g; const tw_t* phi = pow_g + (1u << h);
     for (uint32_t w = tid; w < nrows << (LOGLC - 4); w += nth) {
         const uint32_t rr = w >> (LOGLC - 4), R = row0 + rr, rho = R & rpp_mask;
         const uint32_t* trow = tile + rr * rowpad;
@@ -674,7 +686,7 @@ __global__ void __launch_bounds__(256) k_ntt_fwd1(uint32_t* out, const uint32_t*
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
                     uint32_t v = x[j];
-                    if (pow_g) { v = fp_mul(v, fp_mul(__ldg(plo + (e & lmask)), __ldg(phi + (e >> h)))); e = (e + estep) & mmask; }
+                    if (pow_g) { v = pow_apply(v, __ldg(plo + (e & lmask)), __ldg(phi + (e >> h))); e = (e + estep) & mmask; }
                     orow[base + j * q] = v;
                 }
             });
@@ -684,8 +696,8 @@ __global__ void __launch_bounds__(256) k_ntt_fwd1(uint32_t* out, const uint32_t*
 // inverse pass B: contiguous rows of Lc values, DIF levels LOGLC..1, in place (out == in allowed), optional scale.
 template <int LOGLC>
 __global__ void __launch_bounds__(256) k_ntt_invb(uint32_t* out, const uint32_t* in, uint32_t rows_per_cta, uint32_t lg_rpp, uint32_t total_rows,
-                                                  size_t in_poly_stride, size_t out_poly_stride, const uint32_t* __restrict__ tw_g,
-                                                  uint32_t scale, const uint32_t* __restrict__ p3lo, const uint32_t* __restrict__ p3hi) {
+                                                  size_t in_poly_stride, size_t out_poly_stride, const tw_t* __restrict__ tw_g,
+                                                  uint32_t scale, const tw_t* __restrict__ p3lo, const tw_t* __restrict__ p3hi) {
     extern __shared__ uint32_t smem[];
     constexpr uint32_t Lc = 1u << LOGLC, rowpad = Lc + (Lc >> 4);
     constexpr int REM = LOGLC - 4;                   // levels after the first radix-16 stage
@@ -736,7 +748,7 @@ __global__ void __launch_bounds__(256) k_ntt_invb(uint32_t* out, const uint32_t*
                     v[j] = scale ? fp_mul(x[j], scale) : x[j];
                     if (p3lo) {   // fused zk_shift (K2): slot holds degree d = bitrev(row) + rows_per_poly * bitrev(pos); multiply by 3^d
                         const uint32_t d = bitrev(R & rpp_mask, lg_rpp) + (bitrev(base + j, LOGLC) << lg_rpp);
-                        v[j] = fp_mul(v[j], fp_mul(__ldg(p3lo + (d & 4095)), __ldg(p3hi + (d >> 12))));
+                        v[j] = pow_apply(v[j], __ldg(p3lo + (d & 4095)), __ldg(p3hi + (d >> 12)));
                     }
                 }
                 if constexpr (KF == 1) *reinterpret_cast<uint2*>(orow + base) = make_uint2(v[0], v[1]);
@@ -748,12 +760,12 @@ __global__ void __launch_bounds__(256) k_ntt_invb(uint32_t* out, const uint32_t*
     }
 }
 
-__global__ void k_zk_shift(uint32_t* __restrict__ io, uint32_t lg_n, size_t total, const uint32_t* __restrict__ p3lo,
-                           const uint32_t* __restrict__ p3hi) {
+__global__ void k_zk_shift(uint32_t* __restrict__ io, uint32_t lg_n, size_t total, const tw_t* __restrict__ p3lo,
+                           const tw_t* __restrict__ p3hi) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const uint32_t d = bitrev((uint32_t)(i & ((1u << lg_n) - 1)), lg_n);
-    io[i] = fp_mul(io[i], fp_mul(p3lo[d & 4095], p3hi[d >> 12]));
+    io[i] = pow_apply(io[i], p3lo[d & 4095], p3hi[d >> 12]);
 }
 
 __global__ void k_bit_reverse(uint32_t* __restrict__ io, uint32_t lg_n, size_t total) {
@@ -780,17 +792,17 @@ static uint32_t split_n1(uint32_t lg) { uint32_t n1 = lg / 2; return n1 > 11 ? 1
 
 template <bool DIF>
 static cudaError_t run_strided(const DeviceTables* T, uint32_t* d, uint32_t logL, uint32_t row_stride, uint32_t ncols, uint32_t count,
-                               size_t poly_stride, const uint32_t* pow_g, uint32_t lg_m, cudaStream_t s) {
+                               size_t poly_stride, const tw_t* pow_g, uint32_t lg_m, cudaStream_t s) {
     uint32_t lgTW = strided_lgTW(logL);
     while ((1u << lgTW) > ncols) lgTW--;
     const uint32_t tiles_per_poly = ncols >> lgTW;
     const uint32_t h = (lg_m + 1) / 2;
-    size_t smem = ((size_t)(1u << logL) << lgTW) * 4 + ((size_t)4 << logL) + (pow_g ? ((size_t)4 << h) + ((size_t)4 << (lg_m - h)) : 0);
-    const uint32_t* twt = DIF ? T->tw_inv : T->tw_fwd;
+    size_t smem = ((size_t)(1u << logL) << lgTW) * 4 + ((size_t)8 << logL) + (pow_g ? ((size_t)8 << h) + ((size_t)8 << (lg_m - h)) : 0);
+    const tw_t* twt = DIF ? T->tw_inv : T->tw_fwd;
     if (logL >= 6 && logL <= 11 && ncols % 8 == 0 && row_stride % 4 == 0 && poly_stride % 4 == 0 && ((uintptr_t)d & 15) == 0 &&
         env_int("B200_NTT_PERSISTENT", 1)) {
         // persistent double-buffered kernel: 2 x (L x 8 words) of shared memory per CTA
-        const size_t sm = (size_t)2 * (((size_t)8 << logL) + ((size_t)8 << logL) / 16) * 4 + ((size_t)4 << logL);
+        const size_t sm = (size_t)2 * (((size_t)8 << logL) + ((size_t)8 << logL) / 16) * 4 + ((size_t)8 << logL);
         const uint32_t tpp = ncols / 8, num_tiles = tpp * count;
         uint32_t per_sm = (uint32_t)(226 * 1024 / (sm + 1024)); if (per_sm > 4) per_sm = 4; if (per_sm < 1) per_sm = 1;
         uint32_t grid = (uint32_t)T->sm_count * per_sm; if (grid > num_tiles) grid = num_tiles;
@@ -822,17 +834,17 @@ static cudaError_t run_strided(const DeviceTables* T, uint32_t* d, uint32_t logL
 
 template <bool DIF>
 static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32_t* in, uint32_t logLc, uint32_t lg_e, uint32_t rows_per_poly,
-                              uint32_t count, size_t in_stride, size_t out_stride, const uint32_t* pow_g, uint32_t lg_m,
-                              uint32_t lg_rows, uint32_t scale, cudaStream_t s, const uint32_t* p3lo = nullptr, const uint32_t* p3hi = nullptr,
+                              uint32_t count, size_t in_stride, size_t out_stride, const tw_t* pow_g, uint32_t lg_m,
+                              uint32_t lg_rows, uint32_t scale, cudaStream_t s, const tw_t* p3lo = nullptr, const tw_t* p3hi = nullptr,
                               bool* shift_done = nullptr) {
     uint32_t rpc = logLc >= 12 ? 1 : (1u << (12 - logLc));
     const uint64_t total_rows = (uint64_t)rows_per_poly * count;
     if (rpc > total_rows) rpc = (uint32_t)total_rows;
     const uint32_t h = (lg_m + 1) / 2;
     const uint32_t Lc = 1u << logLc;
-    size_t smem = (size_t)rpc * (Lc + (Lc >> 4)) * 4 + (size_t)Lc * 4 + (pow_g ? ((size_t)4 << h) + ((size_t)4 << (lg_m - h)) : 0);
+    size_t smem = ((size_t)rpc * (Lc + (Lc >> 4)) + 2) * 4 + (size_t)Lc * 8 + (pow_g ? ((size_t)8 << h) + ((size_t)8 << (lg_m - h)) : 0);
     const uint32_t grid = (uint32_t)((total_rows + rpc - 1) / rpc);
-    const uint32_t* twt = DIF ? T->tw_inv : T->tw_fwd;
+    const tw_t* twt = DIF ? T->tw_inv : T->tw_fwd;
     uint32_t lg_rpp = 0; while ((1u << lg_rpp) < rows_per_poly) lg_rpp++;
     if (logLc >= 8 && logLc <= 13 && (DIF ? lg_e == 0 : (lg_e == 2 || lg_e == 0)) && (1u << lg_rpp) == rows_per_poly && env_int("B200_NTT_FUSED", 1) &&
         (((uintptr_t)in | (uintptr_t)out) & 15) == 0 && in_stride % 4 == 0 && out_stride % 4 == 0) {

@@ -39,10 +39,16 @@ void set_error(const char* fmt, ...) {
 static std::mutex g_mu;
 static DeviceTables* g_tables[64];
 
-static uint32_t* upload(const std::vector<uint32_t>& v) {
-    uint32_t* d = nullptr;
-    if (cudaMalloc(&d, v.size() * 4) != cudaSuccess) return nullptr;
-    if (cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+// tables are built in Montgomery form and uploaded as Shoup pairs {plain w, floor(w * 2^32 / p)}
+static uint2* upload(const std::vector<uint32_t>& mont) {
+    std::vector<uint2> v(mont.size());
+    for (size_t i = 0; i < mont.size(); i++) {
+        const uint32_t w = h_from_mont(mont[i]);
+        v[i] = make_uint2(w, (uint32_t)(((uint64_t)w << 32) / HP));
+    }
+    uint2* d = nullptr;
+    if (cudaMalloc(&d, v.size() * sizeof(uint2)) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, v.data(), v.size() * sizeof(uint2), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
     return d;
 }
 
@@ -67,7 +73,7 @@ const DeviceTables* get_tables(int device) {
             uint32_t w = inv ? T->rou_rev[l] : T->rou_fwd[l], cur = h_to_mont(1);
             for (uint32_t i = 0; i < (1u << (l - 1)); i++) { tw[(1u << (l - 1)) + i] = cur; cur = h_mul(cur, w); }
         }
-        uint32_t* d = upload(tw);
+        uint2* d = upload(tw);
         ok &= d != nullptr;
         (inv ? T->tw_inv : T->tw_fwd) = d;
     }
@@ -82,7 +88,7 @@ const DeviceTables* get_tables(int device) {
             const uint32_t wh = h_pow(w, (uint64_t)1 << h);
             cur = inv ? h_inv(h_to_mont(1u << m)) : h_to_mont(1);      // fold 1/2^m into the inverse hi table
             for (uint32_t i = 0; i < (1u << (m - h)); i++) { t[((size_t)1 << h) + i] = cur; cur = h_mul(cur, wh); }
-            uint32_t* d = upload(t);
+            uint2* d = upload(t);
             ok &= d != nullptr;
             (inv ? T->pow_inv : T->pow_fwd)[m] = d;
         }
