@@ -142,10 +142,14 @@ def kernel_roofline(torch, L, pk):
     roof = {"kernel": "k_p2_rows (K4, data group 2^22 x 208)", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": ach / pk["hbm_gbs"], "traffic": traffic, "ms_per_launch": ms, "alg_bytes_per_launch": alg_bytes}
     # the honest bound for this kernel is the INT32 pipe (SURVEY finding 8): report it beside the HBM figure
-    gmul = perms * 1356 / (ms * 1e-3) / 1e9
+    # per permutation: 852 variable x variable Montgomery multiplies (10 multiplier-pipe cycles each) + 504 multiplies by the
+    # diagonal constants done Shoup-style (8 cycles): counted as 0.8 of a Montgomery multiply so that the cheaper formulation
+    # does not flatter the fraction
+    MONT_EQ_PER_PERM = 852 + 0.8 * 504
+    gmul = perms * MONT_EQ_PER_PERM / (ms * 1e-3) / 1e9
     INT_PEAK = 3508.0   # Gmulmod/s, independent-chain Montgomery microbenchmark on this part (profiles/microbench_r01.txt)
-    roof_int = {"kernel": roof["kernel"], "bound": "int32", "achieved": gmul, "peak": INT_PEAK, "unit": "Gmulmod/s",
-                "frac": gmul / INT_PEAK, "gperm_per_s": perms / (ms * 1e-3) / 1e9}
+    roof_int = {"kernel": roof["kernel"], "bound": "int32", "achieved": gmul, "peak": INT_PEAK, "unit": "Gmulmod/s (Montgomery-equivalent)",
+                "frac": gmul / INT_PEAK, "gperm_per_s": perms / (ms * 1e-3) / 1e9, "mont_equiv_per_perm": MONT_EQ_PER_PERM}
     del m, out
     # NTT kernels (HBM-bound): expand+NTT of 16 columns 2^20 -> 2^22, and iNTT of 16 x 2^20
     n, cnt = PO2, 16
@@ -166,9 +170,10 @@ def kernel_roofline(torch, L, pk):
         {"kernel": "iNTT 16 x 2^20 (K1)", "ms": ms_i, "alg_gbs": 8.0 * cnt * (1 << n) / (ms_i * 1e-3) / 1e9},
     ]
     # both transforms are two 10-level passes: 5 butterfly + 2 inter-pass-twiddle multiplies per element in the first pass of each
-    # pair, 5 in the second -> 12 Montgomery multiplies per (output) element: on B200 that, not HBM, is the binding roofline
-    kernels[0]["gmulmod_s"] = 12.0 * cnt * (4 << n) / (ms_e * 1e-3) / 1e9
-    kernels[1]["gmulmod_s"] = 12.0 * cnt * (1 << n) / (ms_i * 1e-3) / 1e9
+    # pair, 5 in the second -> 12 multiplies per (output) element, all by table constants (Shoup, 0.8 of a Montgomery multiply
+    # in multiplier-pipe cycles): on B200 that pipe, not HBM, is the binding roofline
+    kernels[0]["gmulmod_s"] = 0.8 * 12.0 * cnt * (4 << n) / (ms_e * 1e-3) / 1e9
+    kernels[1]["gmulmod_s"] = 0.8 * 12.0 * cnt * (1 << n) / (ms_i * 1e-3) / 1e9
     for k in kernels:
         k["frac_of_hbm_peak"] = k["alg_gbs"] / pk["hbm_gbs"]
         k["frac_of_int32_roofline"] = k["gmulmod_s"] / 3508.0

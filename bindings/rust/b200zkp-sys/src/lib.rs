@@ -44,6 +44,28 @@ extern "C" {
     pub fn b200_batch_evaluate_any(d_out: *mut u32, d_coeffs: *const u32, lg_n: u32, count: u32, d_x: *const u32,
                                    d_scratch: *mut u32, stream: *mut c_void) -> *const c_char;
 
+    // small HAL operations (mix_poly_coeffs, eltwise_*, supra_poly_divide, prefix_products, gather_sample, scatter, Merkle opening)
+    pub fn b200_shutdown() -> *const c_char;
+    pub fn b200_mix_poly_coeffs(d_out: *mut u32, d_mix_start: *const u32, d_mix: *const u32, d_in: *const u32, d_combos: *const u32,
+                                input_size: u32, count: u32, n_combos: u32, stream: *mut c_void) -> *const c_char;
+    pub fn b200_eltwise_sum_extelem(d_out: *mut u32, d_in: *const u32, count: u32, to_add: u32, stream: *mut c_void) -> *const c_char;
+    pub fn b200_poly_divide_scratch_words(size: u32) -> usize;
+    pub fn b200_poly_divide(d_poly: *mut u32, size: u32, d_remainder: *mut u32, d_pow: *const u32, d_scratch: *mut u32,
+                            stream: *mut c_void) -> *const c_char;
+    pub fn b200_prefix_products_scratch_words(count: u32) -> usize;
+    pub fn b200_prefix_products(d_io: *mut u32, count: u32, d_scratch: *mut u32, stream: *mut c_void) -> *const c_char;
+    pub fn b200_eltwise_add_elem(d_out: *mut u32, d_a: *const u32, d_b: *const u32, count: usize, stream: *mut c_void) -> *const c_char;
+    pub fn b200_eltwise_copy_elem(d_out: *mut u32, d_in: *const u32, count: usize, stream: *mut c_void) -> *const c_char;
+    pub fn b200_eltwise_zeroize_elem(d_io: *mut u32, count: usize, stream: *mut c_void) -> *const c_char;
+    pub fn b200_gather_sample(d_dst: *mut u32, d_src: *const u32, idx: usize, size: u32, stride: usize, stream: *mut c_void) -> *const c_char;
+    pub fn b200_scatter(d_into: *mut u32, d_index: *const u32, n_index: u32, d_offsets: *const u32, d_values: *const u32,
+                        n_values: u32, stream: *mut c_void) -> *const c_char;
+    pub fn b200_merkle_open_words(lg_rows: u32, cols: u32, top_size: u32) -> usize;
+    pub fn b200_merkle_open(d_out: *mut u32, d_nodes: *const u32, d_matrix: *const u32, lg_rows: u32, cols: u32, top_size: u32,
+                            idx: u32, stream: *mut c_void) -> *const c_char;
+    pub fn b200_commit_group(d_coeffs_io: *mut u32, d_evals: *mut u32, d_nodes: *mut u32, lg_n: u32, count: u32,
+                             stream: *mut c_void) -> *const c_char;
+
     // operator level (ProverServer::prove_segment / lift / join / resolve / union)
     pub fn b200_seal_words(c: *const b200_circuit) -> usize;
     pub fn b200_prover_create(out: *mut *mut b200_prover, device: c_int, max_circuit: *const b200_circuit, slots: u32) -> *const c_char;

@@ -91,6 +91,13 @@ __device__ __forceinline__ uint32_t fp_pow(uint32_t a, uint64_t e) {
 
 struct Fp4 { uint32_t c[4]; };
 
+__device__ __forceinline__ Fp4 ld_fp4(const uint32_t* p) {        // 16-byte aligned AoS element
+    uint4 v = *reinterpret_cast<const uint4*>(p);
+    return Fp4{{v.x, v.y, v.z, v.w}};
+}
+__device__ __forceinline__ void st_fp4(uint32_t* p, const Fp4& a) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(a.c[0], a.c[1], a.c[2], a.c[3]);
+}
 __device__ __forceinline__ Fp4 fp4_zero() { return Fp4{{0u, 0u, 0u, 0u}}; }
 __device__ __forceinline__ Fp4 fp4_one() { return Fp4{{R1, 0u, 0u, 0u}}; }
 __device__ __forceinline__ Fp4 fp4_add(const Fp4& a, const Fp4& b) {

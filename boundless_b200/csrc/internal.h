@@ -38,6 +38,7 @@ struct DeviceTables {
     uint32_t rou_fwd[28], rou_rev[28];  // host copies, Montgomery
 };
 const DeviceTables* get_tables(int device);   // lazily built, thread-safe; nullptr + error string on failure
+void free_tables();                           // b200_shutdown
 const char* last_error();
 void set_error(const char* fmt, ...);
 
@@ -113,6 +114,10 @@ struct DeepArgs {
     uint32_t lg_n, W, w_accum;
 };
 cudaError_t launch_deep(const DeepArgs& a, cudaStream_t s);
+// supra_poly_divide: Fp4 polynomial (AoS, natural coefficient order) /= (x - *d_pow) in place; *d_remainder = P(*d_pow)
+size_t poly_divide_scratch_words(uint32_t size);
+cudaError_t launch_poly_divide(uint32_t* d_poly, uint32_t size, uint32_t* d_remainder, const uint32_t* d_pow, uint32_t* d_scratch,
+                               cudaStream_t s);
 // K9: gather one Merkle opening per (query, tree) into the seal
 struct GatherTree {
     const uint32_t* matrix; const uint32_t* nodes; uint32_t rows, cols, top_size; uint32_t seal_off;  // offset within a query record

@@ -11,13 +11,6 @@
 
 namespace b200 {
 
-__device__ __forceinline__ Fp4 ld_fp4(const uint32_t* p) {
-    uint4 v = *reinterpret_cast<const uint4*>(p);
-    return Fp4{{v.x, v.y, v.z, v.w}};
-}
-__device__ __forceinline__ void st_fp4(uint32_t* p, const Fp4& a) {
-    *reinterpret_cast<uint4*>(p) = make_uint4(a.c[0], a.c[1], a.c[2], a.c[3]);
-}
 
 // ---- witgen stand-in: element idx = splitmix64(seed, idx) mod p, Montgomery form -----------------------
 __global__ void k_gen_trace(uint32_t* __restrict__ out, uint64_t seed, uint64_t count, const uint32_t* __restrict__ seed_words) {
@@ -288,7 +281,7 @@ __global__ void __launch_bounds__(DV_T) k_deep_chunk_vals(uint32_t* __restrict__
 }
 // (3) carry into chunk k from above: B_k = sum_{m>k} V_m a^(CH*(m-k-1)); one thread per point (nchunks <= ~2048)
 __global__ void k_deep_chunk_scan(uint32_t* __restrict__ carry, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ pts,
-                                  uint32_t nchunks) {
+                                  uint32_t nchunks, uint32_t* __restrict__ rem) {
     const uint32_t pt = blockIdx.x;
     const Fp4 ach = fp4_pow(ld_fp4(pts + 4 * pt), DV_CH);
     Fp4 b = fp4_zero();
@@ -296,6 +289,7 @@ __global__ void k_deep_chunk_scan(uint32_t* __restrict__ carry, const uint32_t* 
         st_fp4(carry + 4 * ((size_t)pt * nchunks + k), b);
         b = fp4_add(fp4_mul(b, ach), ld_fp4(vals + 4 * ((size_t)pt * nchunks + k)));
     }
+    if (rem) st_fp4(rem + 4 * pt, b);      // value of the whole polynomial at the point = remainder of the division
 }
 // (4) quotients of the three points summed, written as 4 planes in bit-reversed order
 __global__ void __launch_bounds__(DV_T) k_deep_divide(uint32_t* __restrict__ planes, const uint32_t* __restrict__ combos,
@@ -362,8 +356,58 @@ cudaError_t launch_deep(const DeepArgs& a, cudaStream_t s) {
     B200_LAUNCH(k_deep_mix)<<<(N + 255) / 256, 256, T * 16, s>>>(a.combos, a.coeffs, a.check_coeffs, a.u, a.mix_pows, a.lg_n, a.W, a.w_accum);
     dim3 g2(nchunks, 3);
     B200_LAUNCH(k_deep_chunk_vals)<<<g2, DV_T, 0, s>>>(a.chunk_vals, a.combos, a.pts, N, nchunks);
-    B200_LAUNCH(k_deep_chunk_scan)<<<3, 1, 0, s>>>(a.chunk_carry, a.chunk_vals, a.pts, nchunks);
+    B200_LAUNCH(k_deep_chunk_scan)<<<3, 1, 0, s>>>(a.chunk_carry, a.chunk_vals, a.pts, nchunks, nullptr);
     B200_LAUNCH(k_deep_divide)<<<nchunks, DV_T, 0, s>>>(a.f_planes, a.combos, a.chunk_carry, a.pts, a.lg_n, nchunks);
+    return cudaGetLastError();
+}
+
+// ---- supra_poly_divide as a standalone operation: one Fp4 polynomial (AoS, natural order) divided in place by (x - z) --------
+__global__ void __launch_bounds__(DV_T) k_poly_divide_apply(uint32_t* __restrict__ poly, const uint32_t* __restrict__ carry,
+                                                            const uint32_t* __restrict__ zp, uint32_t N) {
+    const uint32_t chunk = blockIdx.x, start = chunk * DV_CH;
+    const uint32_t cnt = N - start < DV_CH ? N - start : DV_CH;
+    const uint32_t t0 = threadIdx.x * DV_E;
+    __shared__ uint32_t sc[DV_T * 4];
+    const Fp4 a = ld_fp4(zp);
+    const Fp4 aE = fp4_pow(a, DV_E);
+    Fp4 c[DV_E];
+    Fp4 v = fp4_zero();
+    const uint32_t m = t0 < cnt ? (cnt - t0 < DV_E ? cnt - t0 : DV_E) : 0;
+#pragma unroll
+    for (int i = (int)DV_E - 1; i >= 0; i--) {
+        c[i] = (uint32_t)i < m ? ld_fp4(poly + 4 * ((size_t)start + t0 + i)) : fp4_zero();
+        v = fp4_add(fp4_mul(v, a), c[i]);
+    }
+    for (int e = 0; e < 4; e++) sc[threadIdx.x * 4 + e] = v.c[e];
+    __syncthreads();
+    Fp4 mult = aE;
+    for (uint32_t off = 1; off < DV_T; off <<= 1) {      // suffix scan S_t = sum_{t' >= t} v_t' a^(E (t' - t))
+        Fp4 add = fp4_zero();
+        const bool has = threadIdx.x + off < DV_T;
+        if (has) add = fp4_mul(ld_fp4(sc + 4 * (threadIdx.x + off)), mult);
+        __syncthreads();
+        if (has) { v = fp4_add(v, add); for (int e = 0; e < 4; e++) sc[threadIdx.x * 4 + e] = v.c[e]; }
+        __syncthreads();
+        mult = fp4_mul(mult, mult);
+    }
+    Fp4 b = (threadIdx.x + 1 < DV_T) ? ld_fp4(sc + 4 * (threadIdx.x + 1)) : fp4_zero();
+    b = fp4_add(b, fp4_mul(ld_fp4(carry + 4 * (size_t)chunk), fp4_pow(aE, DV_T - 1 - threadIdx.x)));
+#pragma unroll
+    for (int i = (int)DV_E - 1; i >= 0; i--) {
+        if ((uint32_t)i < m) st_fp4(poly + 4 * ((size_t)start + t0 + i), b);
+        b = fp4_add(c[i], fp4_mul(b, a));
+    }
+}
+size_t poly_divide_scratch_words(uint32_t size) { return (size_t)8 * ((size + DV_CH - 1) / DV_CH) + 8; }
+cudaError_t launch_poly_divide(uint32_t* d_poly, uint32_t size, uint32_t* d_remainder, const uint32_t* d_pow, uint32_t* d_scratch,
+                               cudaStream_t s) {
+    if (size == 0) return cudaMemsetAsync(d_remainder, 0, 16, s);
+    const uint32_t nchunks = (size + DV_CH - 1) / DV_CH;
+    uint32_t* vals = d_scratch;
+    uint32_t* carry = d_scratch + (size_t)4 * nchunks;
+    B200_LAUNCH(k_deep_chunk_vals)<<<dim3(nchunks, 1), DV_T, 0, s>>>(vals, d_poly, d_pow, size, nchunks);
+    B200_LAUNCH(k_deep_chunk_scan)<<<1, 1, 0, s>>>(carry, vals, d_pow, nchunks, d_remainder);
+    B200_LAUNCH(k_poly_divide_apply)<<<nchunks, DV_T, 0, s>>>(d_poly, carry, d_pow, size);
     return cudaGetLastError();
 }
 

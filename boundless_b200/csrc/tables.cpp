@@ -110,4 +110,21 @@ const DeviceTables* get_tables(int device) {
     return T;
 }
 
+// b200_shutdown(): release every device table (callers must have destroyed their provers first)
+void free_tables() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int prev = 0; cudaGetDevice(&prev);
+    for (int dev = 0; dev < 64; dev++) {
+        DeviceTables* T = g_tables[dev];
+        if (!T) continue;
+        if (cudaSetDevice(dev) == cudaSuccess) {
+            cudaFree(T->tw_fwd); cudaFree(T->tw_inv); cudaFree(T->p3lo); cudaFree(T->p3hi);
+            for (int m = 0; m <= MAX_LG; m++) { cudaFree(T->pow_fwd[m]); cudaFree(T->pow_inv[m]); }
+        }
+        delete T;
+        g_tables[dev] = nullptr;
+    }
+    cudaSetDevice(prev);
+}
+
 }  // namespace b200

@@ -45,6 +45,21 @@ SYMBOLS = {
     "b200_fri_fold": (_cp, [_vp, _vp, _u32, _vp, _vp]),
     "b200_evaluate_scratch_words": (_sz, [_u32, _u32]),
     "b200_batch_evaluate_any": (_cp, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),
+    "b200_shutdown": (_cp, []),
+    "b200_mix_poly_coeffs": (_cp, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp]),
+    "b200_eltwise_sum_extelem": (_cp, [_vp, _vp, _u32, _u32, _vp]),
+    "b200_poly_divide_scratch_words": (_sz, [_u32]),
+    "b200_poly_divide": (_cp, [_vp, _u32, _vp, _vp, _vp, _vp]),
+    "b200_prefix_products_scratch_words": (_sz, [_u32]),
+    "b200_prefix_products": (_cp, [_vp, _u32, _vp, _vp]),
+    "b200_eltwise_add_elem": (_cp, [_vp, _vp, _vp, _sz, _vp]),
+    "b200_eltwise_copy_elem": (_cp, [_vp, _vp, _sz, _vp]),
+    "b200_eltwise_zeroize_elem": (_cp, [_vp, _sz, _vp]),
+    "b200_gather_sample": (_cp, [_vp, _vp, _sz, _u32, _sz, _vp]),
+    "b200_scatter": (_cp, [_vp, _vp, _u32, _vp, _vp, _u32, _vp]),
+    "b200_merkle_open_words": (_sz, [_u32, _u32, _u32]),
+    "b200_merkle_open": (_cp, [_vp, _vp, _vp, _u32, _u32, _u32, _u32, _vp]),
+    "b200_commit_group": (_cp, [_vp, _vp, _vp, _u32, _u32, _vp]),
     "b200_seal_words": (_sz, [C.POINTER(Circuit)]),
     "b200_prover_create": (_cp, [C.POINTER(_vp), C.c_int, C.POINTER(Circuit), _u32]),
     "b200_prover_destroy": (None, [_vp]),

@@ -35,6 +35,8 @@ const char* b200_init(int device);
 const char* b200_last_error(void);
 /* number of CUDA devices visible, or -1 (never touches the CPU path) */
 int b200_device_count(void);
+/* frees the per-device twiddle tables built by b200_init (destroy every b200_prover first) */
+const char* b200_shutdown(void);
 
 /* ---- kernel 1: NTT (replaces sppark_batch_iNTT / _NTT / _expand / _zk_shift) ------------------------------ */
 /* K1: `count` in-place iNTTs of size 2^lg_n: natural-order evaluations -> bit-reversed coefficients, x 2^-lg_n */
@@ -65,6 +67,41 @@ const char* b200_fri_fold(uint32_t* d_out, const uint32_t* d_in, uint32_t in_siz
 size_t b200_evaluate_scratch_words(uint32_t lg_n, uint32_t count);
 const char* b200_batch_evaluate_any(uint32_t* d_out, const uint32_t* d_coeffs, uint32_t lg_n, uint32_t count,
                                     const uint32_t* d_x, uint32_t* d_scratch, void* stream);
+
+/* ---- the small HAL operations (K8, K9 and element-wise helpers; replace the risc0-sys C wrappers of SURVEY.md 8b) -------- */
+/* ExtElem buffers are arrays of 4 Montgomery words (16-byte aligned); Elem buffers are plain word arrays.
+ * K8a Hal::mix_poly_coeffs: d_out[combos[i]*count + idx] += mix_start * mix^i * d_in[i*count + idx]   (i < input_size, idx < count)
+ *     d_out = n_combos*count ExtElems (accumulated into), d_mix_start / d_mix = one ExtElem each (device), d_combos = input_size
+ *     words, each < n_combos (other entries are skipped).  input_size <= 10240. */
+const char* b200_mix_poly_coeffs(uint32_t* d_out, const uint32_t* d_mix_start, const uint32_t* d_mix, const uint32_t* d_in,
+                                 const uint32_t* d_combos, uint32_t input_size, uint32_t count, uint32_t n_combos, void* stream);
+/* K8b Hal::eltwise_sum_extelem: d_out[j*count + idx] = (sum_{i<to_add} d_in[i*count + idx]).elems[j]   (ExtElems in, 4 planes out) */
+const char* b200_eltwise_sum_extelem(uint32_t* d_out, const uint32_t* d_in, uint32_t count, uint32_t to_add, void* stream);
+/* K8c supra_poly_divide: ExtElem polynomial (natural coefficient order) /= (x - *d_pow) in place, *d_remainder = P(*d_pow).
+ *     d_scratch = b200_poly_divide_scratch_words(size) words, 16-byte aligned. */
+size_t b200_poly_divide_scratch_words(uint32_t size);
+const char* b200_poly_divide(uint32_t* d_poly, uint32_t size, uint32_t* d_remainder, const uint32_t* d_pow, uint32_t* d_scratch,
+                             void* stream);
+/* Hal::prefix_products: d_io[i] = d_io[0] * ... * d_io[i] over `count` ExtElems (the accum grand product, X2) */
+size_t b200_prefix_products_scratch_words(uint32_t count);
+const char* b200_prefix_products(uint32_t* d_io, uint32_t count, uint32_t* d_scratch, void* stream);
+/* Hal::eltwise_add_elem / eltwise_copy_elem / eltwise_zeroize_elem (zeroize: the INVALID marker 0xFFFFFFFF becomes 0) */
+const char* b200_eltwise_add_elem(uint32_t* d_out, const uint32_t* d_a, const uint32_t* d_b, size_t count, void* stream);
+const char* b200_eltwise_copy_elem(uint32_t* d_out, const uint32_t* d_in, size_t count, void* stream);
+const char* b200_eltwise_zeroize_elem(uint32_t* d_io, size_t count, void* stream);
+/* K9 Hal::gather_sample: d_dst[g] = d_src[g*stride + idx], g < size */
+const char* b200_gather_sample(uint32_t* d_dst, const uint32_t* d_src, size_t idx, uint32_t size, size_t stride, void* stream);
+/* Hal::scatter: d_into[d_offsets[k]] = d_values[k] for k in [d_index[0], d_index[n_index-1]); n_values bounds the launch */
+const char* b200_scatter(uint32_t* d_into, const uint32_t* d_index, uint32_t n_index, const uint32_t* d_offsets,
+                         const uint32_t* d_values, uint32_t n_values, void* stream);
+/* K9 MerkleTreeProver::prove(idx): d_out = the `cols` values of row idx, then the sibling digests from the leaf layer up to (not
+ *     including) the layer of top_size nodes; b200_merkle_open_words gives the length.  d_nodes as built by b200_merkle_tree. */
+size_t b200_merkle_open_words(uint32_t lg_rows, uint32_t cols, uint32_t top_size);
+const char* b200_merkle_open(uint32_t* d_out, const uint32_t* d_nodes, const uint32_t* d_matrix, uint32_t lg_rows, uint32_t cols,
+                             uint32_t top_size, uint32_t idx, void* stream);
+/* composite PolyGroup::new: d_coeffs_io = count columns of 2^lg_n evaluations -> shifted bit-reversed coefficients (K1+K2);
+ *     d_evals = count x 2^(lg_n+2) evaluations (K3); d_nodes = 2 * 2^(lg_n+2) digests, root = node 1 (K4+K5) */
+const char* b200_commit_group(uint32_t* d_coeffs_io, uint32_t* d_evals, uint32_t* d_nodes, uint32_t lg_n, uint32_t count, void* stream);
 
 /* ---- prover pipeline (the ProverServer operator boundary) ------------------------------------------------------- */
 typedef struct {

@@ -59,6 +59,18 @@ typedef struct {
 void oracle_merkle_build(fp *nodes /* 2*rows*8 */, const fp *matrix, size_t rows, size_t cols);   /* K4+K5 */
 void oracle_fri_fold(fp *out, const fp *in, size_t in_size, fp4 mix);                             /* K6 */
 void oracle_batch_evaluate_any(fp4 *out, const fp *coeffs, unsigned n, size_t count, fp4 x);      /* K7 */
+/* ---- small HAL operations (halops.c): K8, K9 and element-wise helpers ---- */
+void oracle_mix_poly_coeffs(fp4 *out, fp4 mix_start, fp4 mix, const fp *in, const uint32_t *combos, size_t input_size, size_t count);
+void oracle_eltwise_sum_extelem(fp *out, const fp4 *in, size_t count, size_t to_add);
+void oracle_eltwise_add_elem(fp *out, const fp *a, const fp *b, size_t count);
+void oracle_eltwise_copy_elem(fp *out, const fp *in, size_t count);
+void oracle_eltwise_zeroize_elem(fp *io, size_t count);
+fp4 oracle_poly_divide(fp4 *p, size_t size, fp4 z);                                    /* returns the remainder P(z) */
+void oracle_prefix_products(fp4 *io, size_t count);
+void oracle_gather_sample(fp *dst, const fp *src, size_t idx, size_t size, size_t stride);
+void oracle_scatter(fp *into, const uint32_t *index, size_t n_index, const uint32_t *offsets, const fp *values);
+size_t oracle_merkle_open(uint32_t *out, const fp *nodes, const fp *matrix, size_t rows, size_t cols, size_t top_size, size_t idx);
+void oracle_commit_group(fp *coeffs, fp *evals, fp *nodes, unsigned n, size_t count);
 void oracle_gen_trace(fp *out, uint64_t seed, unsigned po2, size_t cols);   /* witgen stand-in (code+data) */
 void oracle_segment_digest(fp *out8, uint64_t seed);
 void oracle_seal_digest(fp *out8, const uint32_t *seal, size_t words);

@@ -18,7 +18,7 @@ QUERIES = 50
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("poseidon2.c", "ntt.c", "stark.c", "bb.h", "oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("poseidon2.c", "ntt.c", "stark.c", "halops.c", "bb.h", "oracle.h", "Makefile")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE], stdout=subprocess.DEVNULL)
     return _SO
@@ -73,11 +73,24 @@ def lib():
             "oracle_gen_trace": [C.c_void_p, C.c_uint64, C.c_uint, C.c_size_t],
             "oracle_segment_digest": [C.c_void_p, C.c_uint64],
             "oracle_seal_digest": [C.c_void_p, C.c_void_p, C.c_size_t],
+            "oracle_mix_poly_coeffs": [C.c_void_p, Fp4, Fp4, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t],
+            "oracle_eltwise_sum_extelem": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t],
+            "oracle_eltwise_add_elem": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t],
+            "oracle_eltwise_copy_elem": [C.c_void_p, C.c_void_p, C.c_size_t],
+            "oracle_eltwise_zeroize_elem": [C.c_void_p, C.c_size_t],
+            "oracle_prefix_products": [C.c_void_p, C.c_size_t],
+            "oracle_gather_sample": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t],
+            "oracle_scatter": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p],
+            "oracle_commit_group": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_size_t],
             "oracle_rng_init": [C.c_void_p],
             "oracle_rng_mix": [C.c_void_p, C.c_void_p],
         }.items():
             getattr(L, name).argtypes = args
             getattr(L, name).restype = None
+        L.oracle_poly_divide.argtypes = [C.c_void_p, C.c_size_t, Fp4]
+        L.oracle_poly_divide.restype = Fp4
+        L.oracle_merkle_open.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]
+        L.oracle_merkle_open.restype = C.c_size_t
         L.oracle_rng_elem.argtypes = [C.c_void_p]
         L.oracle_rng_elem.restype = C.c_uint32
         L.oracle_p2_init()
@@ -198,6 +211,75 @@ def batch_evaluate_any(coeffs, n, count, x):
     out = np.zeros(count * 4, np.uint32)
     lib().oracle_batch_evaluate_any(_p(out), _p(a), n, count, fp4(x))
     return out.reshape(count, 4)
+
+
+def mix_poly_coeffs(out, mix_start, mix, inp, combos, input_size, count):
+    """out: (n_combos*count, 4) accumulated into (copy returned)."""
+    o = _u32(out).copy(); a = _u32(inp); c = _u32(combos)
+    lib().oracle_mix_poly_coeffs(_p(o), fp4(mix_start), fp4(mix), _p(a), _p(c), input_size, count)
+    return o
+
+
+def eltwise_sum_extelem(inp, count, to_add):
+    a = _u32(inp)
+    out = np.zeros(4 * count, np.uint32)
+    lib().oracle_eltwise_sum_extelem(_p(out), _p(a), count, to_add)
+    return out
+
+
+def eltwise_add_elem(a, b):
+    a = _u32(a); b = _u32(b)
+    out = np.zeros(a.size, np.uint32)
+    lib().oracle_eltwise_add_elem(_p(out), _p(a), _p(b), a.size)
+    return out
+
+
+def eltwise_zeroize_elem(io):
+    a = _u32(io).copy()
+    lib().oracle_eltwise_zeroize_elem(_p(a), a.size)
+    return a
+
+
+def poly_divide(poly, z):
+    """poly: (size, 4) natural-order Fp4 coefficients.  Returns (quotient array, remainder[4])."""
+    a = _u32(poly).copy()
+    r = lib().oracle_poly_divide(_p(a), a.size // 4, fp4(z))
+    return a, np.array(list(r.c), np.uint32)
+
+
+def prefix_products(io):
+    a = _u32(io).copy()
+    lib().oracle_prefix_products(_p(a), a.size // 4)
+    return a
+
+
+def gather_sample(src, idx, size, stride):
+    a = _u32(src)
+    out = np.zeros(size, np.uint32)
+    lib().oracle_gather_sample(_p(out), _p(a), idx, size, stride)
+    return out
+
+
+def scatter(into, index, offsets, values):
+    o = _u32(into).copy(); i = _u32(index); f = _u32(offsets); v = _u32(values)
+    lib().oracle_scatter(_p(o), _p(i), i.size, _p(f), _p(v))
+    return o
+
+
+def merkle_open(nodes, matrix, rows, cols, top_size, idx):
+    n = _u32(nodes); m = _u32(matrix)
+    out = np.zeros(cols + 8 * 32, np.uint32)
+    w = lib().oracle_merkle_open(_p(out), _p(n), _p(m), rows, cols, top_size, idx)
+    return out[:w].copy()
+
+
+def commit_group(cols_evals, n, count):
+    """Returns (coeffs, evals, nodes) of PolyGroup::new over `count` columns of 2^n evaluations."""
+    co = _u32(cols_evals).copy()
+    ev = np.zeros(count << (n + 2), np.uint32)
+    nodes = np.zeros(2 * (1 << (n + 2)) * 8, np.uint32)
+    lib().oracle_commit_group(_p(co), _p(ev), _p(nodes), n, count)
+    return co, ev, nodes
 
 
 def gen_trace(seed, po2, cols):
