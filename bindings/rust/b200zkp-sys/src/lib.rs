@@ -75,6 +75,7 @@ extern "C" {
                                     h_seal: *mut u32) -> *const c_char;
     pub fn b200_recursion_async(p: *mut b200_prover, slot: u32, c: *const b200_circuit, h_seal_a: *const u32, words_a: usize,
                                 h_seal_b: *const u32, words_b: usize, h_seal: *mut u32) -> *const c_char;
+    pub fn b200_verify_async(p: *mut b200_prover, slot: u32, h_seal: *const u32, words: usize, h_result: *mut c_int) -> *const c_char;
     pub fn b200_prover_wait(p: *mut b200_prover, slot: u32) -> *const c_char;
     pub fn b200_prover_last_ms(p: *mut b200_prover, slot: u32) -> f32;
     pub fn b200_prover_mark(p: *mut b200_prover, slot: u32, which: u32) -> *const c_char;

@@ -5,5 +5,5 @@ reference's operator interface; nothing here (or in the library) falls back to t
 """
 from .lib import B200Error, Circuit, load, require_gpu  # noqa: F401
 from .planner import Planner, PlannerErr  # noqa: F401
-from .prover_server import (ProverOpts, ProverServer, Segment, SegmentReceipt, SuccinctReceipt, VerifierContext,  # noqa: F401
-                            get_prover_server)
+from .prover_server import (ProverOpts, ProverServer, Segment, SegmentReceipt, SuccinctReceipt, VerificationError,  # noqa: F401
+                            VerifierContext, get_prover_server)

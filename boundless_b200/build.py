@@ -13,7 +13,7 @@ OBJ = os.path.join(HERE, "_obj")
 SO = os.path.join(HERE, "libb200zkp.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-SOURCES = ["ntt.cu", "hash.cu", "stark.cu", "halops.cu", "tables.cpp", "prover.cpp", "capi.cpp", "planner.cpp"]
+SOURCES = ["ntt.cu", "hash.cu", "stark.cu", "halops.cu", "verify.cu", "tables.cpp", "prover.cpp", "capi.cpp", "planner.cpp"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-ccbin", HOSTCXX,
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-I", CSRC, "-I", os.path.join(HERE, "..", "include")]
 

@@ -126,4 +126,24 @@ struct GatherTree {
 cudaError_t launch_gather_queries(uint32_t* d_seal, uint32_t query_base, uint32_t query_words, const uint32_t* d_pos,
                                   const GatherTree* d_trees, uint32_t n_trees, cudaStream_t s);
 
+// ---- seal verification (verify.cu) ----------------------------------------------------------------------------
+// device context words: verdicts, DEEP sums and a scratch root
+constexpr uint32_t VCTX_WORDS = 128, VCTX_RC = 0, VCTX_RESULT = 1, VCTX_QRC = 2 /* .. 2+QUERIES */, VCTX_USUM = 64 /* 3 Fp4 */, VCTX_ROOT = 80;
+struct VerifyShape {
+    uint32_t po2, w_code, w_data, w_accum, W, T, rounds, final_size, final_lg;
+    uint32_t off_top[4], off_u, off_fri_top[8], off_final, off_queries, query_words, q_off_group[4], q_off_fri[8];
+    uint32_t fri_rows[8], fri_top[8];
+    uint32_t rou_fwd[28];      // Montgomery
+    uint32_t inv16;            // Montgomery 1/16
+};
+cudaError_t launch_verify_reset(uint32_t* ctx, cudaStream_t s);
+cudaError_t launch_verify_canonical(uint32_t* ctx, const uint32_t* seal, uint32_t words, cudaStream_t s);
+cudaError_t launch_verify_fold_top(uint32_t* root_out, const uint32_t* top, uint32_t top_size, cudaStream_t s);
+cudaError_t launch_verify_constraint(uint32_t* ctx, const uint32_t* u, const uint32_t* pm, const uint32_t* z, uint32_t w_code,
+                                     uint32_t w_data, uint32_t w_accum, cudaStream_t s);
+cudaError_t launch_verify_usum(uint32_t* ctx, const uint32_t* u, const uint32_t* mp, uint32_t W, uint32_t w_accum, uint32_t T, cudaStream_t s);
+cudaError_t launch_verify_queries(uint32_t* ctx, const uint32_t* seal, const VerifyShape& sh, const uint32_t* mp, const uint32_t* pts,
+                                  const uint32_t* fmix, const uint32_t* pos, cudaStream_t s);
+cudaError_t launch_verify_finish(uint32_t* ctx, cudaStream_t s);
+
 }  // namespace b200

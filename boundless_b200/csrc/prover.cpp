@@ -87,13 +87,14 @@ struct Slot {
     uint32_t *coeffs, *evals, *check_coeffs, *check_evals, *nodes[4];
     uint32_t *fri_evals, *fri_nodes, *fri_coeffs;
     uint32_t *combos, *f_planes, *chunk_vals, *chunk_carry, *ev_scratch;
-    uint32_t *pmix, *mp, *chal, *pts, *pos, *seal, *digests;
+    uint32_t *pmix, *mp, *chal, *pts, *pos, *seal, *digests, *vctx;
     Transcript* tr;
     GatherTree* d_trees;
     std::vector<GatherTree> h_trees;
     uint32_t* h_seal_out = nullptr; size_t seal_words = 0;
     uint32_t* h_stage = nullptr; size_t h_stage_words = 0;   // pinned staging for child seals
     bool busy = false;
+    b200_circuit last_circuit{}; bool has_seal = false;     // what s.seal holds (for verify of the slot's own proof)
 };
 
 }  // namespace b200
@@ -121,7 +122,7 @@ static size_t arena_words(const b200_circuit& c) {
     add(evaluate_scratch_words(c.po2, (uint32_t)W));
     add(4 * (W / 4 + c.w_accum)); add(4 * (W + c.w_accum + CHECK_COLS)); add(64); add(16); add(64);
     add(SealLayout(c).total); add(64);
-    add(sizeof(Transcript) / 4); add(16 * sizeof(GatherTree) / 4);
+    add(sizeof(Transcript) / 4); add(16 * sizeof(GatherTree) / 4); add(VCTX_WORDS);
     return w + 1024;
 }
 
@@ -147,6 +148,7 @@ static const char* slot_init(b200_prover* p, Slot& s) {
     s.seal = a.take(SealLayout(c).total); s.digests = a.take(64);
     s.tr = reinterpret_cast<Transcript*>(a.take(sizeof(Transcript) / 4));
     s.d_trees = reinterpret_cast<GatherTree*>(a.take(16 * sizeof(GatherTree) / 4));
+    s.vctx = a.take(VCTX_WORDS);
     if (a.used > a.words) { set_error("b200: arena overflow (%zu > %zu words)", a.used, a.words); return last_error(); }
     return nullptr;
 }
@@ -257,6 +259,71 @@ static const char* prove_on_slot(b200_prover* p, Slot& s, const b200_circuit& c,
     CU(cudaMemcpyAsync(h_seal, s.seal, (size_t)L.total * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(s.ev_end, st));
     s.busy = true; s.h_seal_out = h_seal; s.seal_words = L.total;
+    s.last_circuit = c; s.has_seal = true;
+    return nullptr;
+}
+
+// verify_integrity of the seal held in s.seal (circuit c): replay the transcript, then check the 50 queries in parallel.
+// Uses the slot's challenge / transcript scratch, so it is ordered after any proof on the same slot by the stream.
+static const char* verify_on_slot(b200_prover* p, Slot& s, const b200_circuit& c, int* h_result) {
+    cudaStream_t st = s.stream;
+    const uint32_t po2 = c.po2, N = 1u << po2, D = 4 * N;
+    const uint32_t W = c.w_code + c.w_data + c.w_accum, T = W + c.w_accum + CHECK_COLS;
+    const SealLayout L(c);
+    VerifyShape sh{};
+    sh.po2 = po2; sh.w_code = c.w_code; sh.w_data = c.w_data; sh.w_accum = c.w_accum; sh.W = W; sh.T = T;
+    sh.rounds = L.rounds; sh.final_size = (uint32_t)L.final_size; sh.final_lg = ilog2(L.final_size);
+    for (int g = 0; g < 4; g++) { sh.off_top[g] = L.off_top[g]; sh.q_off_group[g] = L.q_off_group[g]; }
+    sh.off_u = L.off_u; sh.off_final = L.off_final; sh.off_queries = L.off_queries; sh.query_words = L.query_words;
+    memcpy(sh.rou_fwd, p->T->rou_fwd, sizeof sh.rou_fwd);
+    sh.inv16 = h_inv(h_to_mont(16));
+    uint32_t* seal = s.seal;
+    uint32_t* accum_mix = s.chal; uint32_t* poly_mix = s.chal + 4; uint32_t* z = s.chal + 8; uint32_t* mix = s.chal + 12;
+    uint32_t* fmix = s.chal + 16;
+    uint32_t* root = s.vctx + VCTX_ROOT;
+    const uint32_t widths[4] = {c.w_code, c.w_data, c.w_accum, (uint32_t)CHECK_COLS};
+
+    KL(launch_verify_reset(s.vctx, st));
+    KL(launch_verify_canonical(s.vctx, seal, L.total, st));
+    KL(launch_iop_init(s.tr, st));
+    KL(launch_iop_commit_elems(s.tr, seal, GLOBALS, nullptr, st));
+    auto commit_top = [&](uint32_t off, uint32_t rows, uint32_t cols) -> const char* {
+        MerkleShape m(rows, cols);
+        KL(launch_verify_fold_top(root, seal + off, m.top_size, st));
+        KL(launch_iop_commit(s.tr, root, st));
+        return nullptr;
+    };
+    const char* e;
+    if ((e = commit_top(L.off_top[0], D, widths[0]))) return e;
+    if ((e = commit_top(L.off_top[1], D, widths[1]))) return e;
+    KL(launch_iop_draw_ext(s.tr, accum_mix, 1, st));          // binds the transcript; accum itself is witness
+    if ((e = commit_top(L.off_top[2], D, widths[2]))) return e;
+    KL(launch_iop_draw_ext(s.tr, poly_mix, 1, st));
+    if ((e = commit_top(L.off_top[3], D, widths[3]))) return e;
+    KL(launch_iop_draw_ext(s.tr, z, 1, st));
+    KL(launch_deep_points(s.pts, z, p->T->rou_rev[po2], st));
+    const uint32_t* u = seal + L.off_u;
+    KL(launch_iop_commit_elems(s.tr, u, T * 4, nullptr, st));
+    KL(launch_powers(s.pmix, poly_mix, W / 4 + c.w_accum, st));
+    KL(launch_verify_constraint(s.vctx, u, s.pmix, z, c.w_code, c.w_data, c.w_accum, st));
+    KL(launch_iop_draw_ext(s.tr, mix, 1, st));
+    KL(launch_powers(s.mp, mix, T, st));
+    KL(launch_verify_usum(s.vctx, u, s.mp, W, c.w_accum, T, st));
+    uint32_t size = N;
+    for (unsigned r = 0; r < L.rounds; r++) {
+        const uint32_t rows = 4 * size / FRI_FOLD;
+        MerkleShape m(rows, 4 * FRI_FOLD);
+        sh.off_fri_top[r] = L.off_fri_top[r]; sh.q_off_fri[r] = L.q_off_fri[r]; sh.fri_rows[r] = rows; sh.fri_top[r] = m.top_size;
+        if ((e = commit_top(L.off_fri_top[r], rows, 4 * FRI_FOLD))) return e;
+        KL(launch_iop_draw_ext(s.tr, fmix + 4 * r, 1, st));
+        size /= FRI_FOLD;
+    }
+    KL(launch_iop_commit_elems(s.tr, seal + L.off_final, 4 * size, nullptr, st));
+    KL(launch_iop_draw_bits(s.tr, s.pos, QUERIES, po2 + 2, st));
+    KL(launch_verify_queries(s.vctx, seal, sh, s.mp, s.pts, fmix, s.pos, st));
+    KL(launch_verify_finish(s.vctx, st));
+    CU(cudaMemcpyAsync(h_result, s.vctx + VCTX_RESULT, 4, cudaMemcpyDeviceToHost, st));
+    s.busy = true;
     return nullptr;
 }
 
@@ -371,6 +438,37 @@ const char* b200_recursion_async(b200_prover* p, uint32_t slot, const b200_circu
     // trace seed = first two words of the input digest
     CU(cudaMemcpyAsync(s.digests, s.seal + 8, 8, cudaMemcpyDeviceToDevice, s.stream));
     return prove_on_slot(p, s, *c, 0, true, nullptr, h_seal);
+}
+
+// verify_integrity: h_seal == NULL verifies the seal the slot produced last (still resident on the device)
+const char* b200_verify_async(b200_prover* p, uint32_t slot, const uint32_t* h_seal, size_t words, int* h_result) {
+    if (!p || slot >= p->slots.size()) { set_error("b200: bad prover/slot"); return last_error(); }
+    if (!h_result) { set_error("b200: null h_result"); return last_error(); }
+    Slot& s = p->slots[slot];
+    b200_circuit c;
+    if (h_seal) {
+        if (s.busy) { set_error("b200: slot %u busy (call b200_prover_wait first)", slot); return last_error(); }
+        if (words < (size_t)GLOBALS) { *h_result = 100; return nullptr; }
+        c = b200_circuit{h_seal[0], h_seal[1], h_seal[2], h_seal[3], h_seal[4]};
+        if (check_circuit(&c)) { *h_result = 101; return nullptr; }
+        if ((size_t)SealLayout(c).total != words) { *h_result = 102; return nullptr; }
+    } else {
+        if (!s.has_seal) { set_error("b200: slot %u holds no seal to verify", slot); return last_error(); }
+        c = s.last_circuit;
+    }
+    if (c.po2 > p->maxc.po2 || c.w_code + c.w_data + c.w_accum > p->maxc.w_code + p->maxc.w_data + p->maxc.w_accum ||
+        c.w_accum > p->maxc.w_accum || SealLayout(c).total > SealLayout(p->maxc).total) {
+        set_error("b200: seal's circuit exceeds the prover's max_circuit"); return last_error();
+    }
+    CU(cudaSetDevice(p->device));
+    if (h_seal) {
+        if (words > s.h_stage_words) { set_error("b200: seal too large for the staging buffer"); return last_error(); }
+        memcpy(s.h_stage, h_seal, words * 4);
+        CU(cudaMemcpyAsync(s.seal, s.h_stage, words * 4, cudaMemcpyHostToDevice, s.stream));
+        s.last_circuit = c; s.has_seal = true;
+    }
+    *h_result = -1;
+    return verify_on_slot(p, s, c, h_result);
 }
 
 const char* b200_prover_wait(b200_prover* p, uint32_t slot) {

@@ -44,6 +44,7 @@ class Segment:
     po2: int = 20
     seed: Optional[int] = None
     trace: Optional[np.ndarray] = None         # optional host witness (w_code + w_data) x 2^po2, Montgomery u32
+    assumptions: list = field(default_factory=list)   # claim digests this segment's guest output depends on (tasks/resolve.rs)
 
     def __post_init__(self):
         if self.seed is None:
@@ -55,6 +56,7 @@ class SegmentReceipt:
     seal: np.ndarray
     index: int
     po2: int
+    assumptions: list = field(default_factory=list)
 
     def get_seal_bytes(self):
         return self.seal.tobytes()
@@ -65,10 +67,24 @@ class SuccinctReceipt:
     seal: np.ndarray
     kind: int
     claim: tuple = field(default_factory=tuple)   # (first_segment, last_segment) covered by this receipt
+    assumptions: list = field(default_factory=list)   # unresolved assumption claim digests (hex), tasks/resolve.rs:47-60
+
+    def claim_digest(self) -> str:
+        """Stand-in for `receipt.claim.digest()` (tasks/resolve.rs:81): identifies this receipt as somebody's assumption."""
+        import hashlib
+        return hashlib.sha256(np.ascontiguousarray(self.seal, dtype="<u4").tobytes()).hexdigest()
 
 
 class VerifierContext:
     """Placeholder for risc0_zkvm::VerifierContext (prove.rs:44): carries nothing on the synthetic path."""
+
+
+class VerificationError(B200Error):
+    """`verify_integrity` failed: the reference's `Err` from `verify_integrity_with_context` (tasks/prove.rs:56-58)."""
+
+    def __init__(self, code):
+        super().__init__("seal does not verify (check %d failed)" % code)
+        self.code = code
 
 
 class _Pinned:
@@ -101,6 +117,7 @@ class ProverServer:
         max_words = max(self.seal_words(self.seg_circuit), self.seal_words(self._rec_circuit(KIND_LIFT)))
         self._seal_bufs = [_Pinned(self.L, max_words) for _ in range(opts.slots)]
         self._pending = [None] * opts.slots
+        self._verdict = [C.c_int(0) for _ in range(opts.slots)]
 
     # -- helpers -------------------------------------------------------------------------------------------
     def _rec_circuit(self, kind):
@@ -165,12 +182,42 @@ class ProverServer:
         what, c, arg, _keep = pend
         seal = self._seal_bufs[slot].array[: self.seal_words(c)].copy()
         if what == "segment":
-            return SegmentReceipt(seal, arg.index, arg.po2)
+            return SegmentReceipt(seal, arg.index, arg.po2, list(arg.assumptions))
         kind, a, b = arg
         lo = a.claim[0] if isinstance(a, SuccinctReceipt) else a.index
+        if kind in (KIND_RESOLVE,):
+            # the conditional receipt keeps its claim; the resolved assumption leaves its list
+            gone = b.claim_digest()
+            return SuccinctReceipt(seal, kind, tuple(a.claim), [x for x in a.assumptions if x != gone])
         last = b if b is not None else a
         hi = last.claim[1] if isinstance(last, SuccinctReceipt) else last.index
-        return SuccinctReceipt(seal, kind, (lo, hi))
+        asm = list(a.assumptions) + (list(b.assumptions) if b is not None and kind == KIND_JOIN else [])
+        return SuccinctReceipt(seal, kind, (lo, hi), asm if kind != KIND_UNION else [])
+
+    # -- verify_integrity on the device (tasks/prove.rs:56-58, :106-108; tasks/join.rs:77-79) ---------------------------
+    def submit_verify(self, slot, receipt=None):
+        """Enqueue the verification of `receipt` (slot must be idle) or, with receipt=None, of the seal the slot is producing
+        (may follow submit_segment / submit_recursion directly: same stream, no host round trip).  wait_verify() gives the verdict."""
+        if receipt is None:
+            _lib.check(self.L.b200_verify_async(self.h, slot, None, 0, C.byref(self._verdict[slot])))
+            return None
+        seal = np.ascontiguousarray(receipt.seal, dtype=np.uint32)
+        _lib.check(self.L.b200_verify_async(self.h, slot, seal.ctypes.data_as(C.c_void_p), seal.size, C.byref(self._verdict[slot])))
+        return seal
+
+    def wait_verify(self, slot):
+        _lib.check(self.L.b200_prover_wait(self.h, slot))
+        code = int(self._verdict[slot].value)
+        if code != 0:
+            raise VerificationError(code)
+
+    def verify_integrity(self, receipt, slot=0):
+        """receipt.verify_integrity_with_context(&ctx): raises VerificationError unless the seal is valid."""
+        if self._pending[slot] is not None:
+            raise B200Error("slot %d busy" % slot)
+        keep = self.submit_verify(slot, receipt)
+        self.wait_verify(slot)
+        del keep
 
     def last_ms(self, slot):
         return float(self.L.b200_prover_last_ms(self.h, slot))

@@ -127,6 +127,13 @@ const char* b200_prove_segment_async(b200_prover* p, uint32_t slot, const b200_c
 /* lift / join / resolve / union: recursion-shaped proof (kind 1..4) over the digest(s) of the child seal(s) */
 const char* b200_recursion_async(b200_prover* p, uint32_t slot, const b200_circuit* c, const uint32_t* h_seal_a,
                                  size_t words_a, const uint32_t* h_seal_b, size_t words_b, uint32_t* h_seal);
+/* verify_integrity (the check the reference runs after every prove / lift / join: tasks/prove.rs:56-58, tasks/join.rs:77-79),
+ * on the device: transcript replay + the 50 queries in parallel.  h_seal == NULL verifies the seal the slot produced last
+ * (still resident; may be enqueued right behind b200_prove_segment_async on a busy slot), otherwise `words` words from host
+ * memory (slot must be idle).  *h_result is valid after b200_prover_wait: 0 = valid, else the code of the first failed check
+ * (100-102 malformed header/length, 106 non-canonical word, 110 constraint identity, 120+g Merkle path of group g,
+ * 130+k / 140+k FRI round k path / value, 150 final polynomial). */
+const char* b200_verify_async(b200_prover* p, uint32_t slot, const uint32_t* h_seal, size_t words, int* h_result);
 const char* b200_prover_wait(b200_prover* p, uint32_t slot);
 /* device time (ms) between the first and last operation of the slot's last proof */
 float b200_prover_last_ms(b200_prover* p, uint32_t slot);

@@ -439,6 +439,7 @@ int oracle_verify(const uint32_t *seal, size_t words) {
     oracle_circuit c = {seal[0], seal[1], seal[2], seal[3], seal[4]};
     if (check_circuit(&c)) return 101;
     if (oracle_seal_words(&c) != words) return 102;
+    if (!valid_elems(seal, words)) return 106;      /* every word of a seal is a canonical field element (header words are small) */
     const unsigned po2 = c.po2;
     const size_t N = (size_t)1 << po2, D = 4 * N;
     const uint32_t W = c.w_code + c.w_data + c.w_accum, T = W + c.w_accum + ORACLE_CHECK_COLS;

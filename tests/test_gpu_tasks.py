@@ -1,0 +1,56 @@
+"""The bento job flow with real device-side proofs and device-side verify_integrity: executor stand-in -> taskdb -> GPU agent
+(tasks/prove.rs, join.rs, resolve.rs) -> aux agent (finalize.rs).  The root receipt must equal, word for word, the one the CPU
+oracle builds for the same job, and must pass the oracle's verifier."""
+import json
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+IMAGE = "cd" * 32
+
+
+def test_job_through_the_agent_loop(gpu, oracle):
+    from boundless_b200 import ProverOpts, get_prover_server, tasks, wire
+    from boundless_b200.prover_server import KIND_JOIN, KIND_LIFT, RECURSION_WIDTHS
+    from boundless_b200.taskdb import MemoryTaskDb
+    n, po2, rp = 3, 9, 11
+    srv = get_prover_server(ProverOpts(segment_po2=12, recursion_po2=rp, slots=1))
+    try:
+        db = MemoryTaskDb()
+        db.create_stream(wire.PROVE_WORK_TYPE, user_id="u"); db.create_stream(wire.AUX_WORK_TYPE, user_id="u")
+        execs = db.create_stream(wire.EXEC_WORK_TYPE, user_id="u")
+        store = tasks.MemoryHotStore()
+        store.set_bytes("input:1", json.dumps({"segments": n, "po2": po2}).encode())
+        job = db.create_job(execs, wire.task_type_to_value(wire.ExecutorReq(image=IMAGE, input="input:1", user_id="u")), user_id="u")
+        launches0 = gpu.cuda.is_available() and srv.L.b200_kernel_launches()
+        assert tasks.poll_work(tasks.Agent(db, store, None, tasks.AgentArgs(task_stream=wire.EXEC_WORK_TYPE))) == 1
+        gpu_agent = tasks.Agent(db, store, srv, tasks.AgentArgs(task_stream=wire.PROVE_WORK_TYPE))
+        assert tasks.poll_work(gpu_agent) == n + (n - 1) + 1
+        assert tasks.poll_work(tasks.Agent(db, store, srv, tasks.AgentArgs(task_stream=wire.AUX_WORK_TYPE))) == 1
+        assert db.job_state(job) == "done", db.job_error(job)
+        assert srv.L.b200_kernel_launches() > launches0
+        root, journal = wire.deserialize_rollup(store.assets["receipts/stark/%s.bincode" % job])
+        assert root.claim == (0, n - 1) and json.loads(journal) == {"segments": n}
+
+        def rec(kind, digest):
+            return oracle.prove(rp, int(digest[0]) | (int(digest[1]) << 32), *RECURSION_WIDTHS, kind=kind, input_digest=digest)
+        lifts = [rec(KIND_LIFT, oracle.seal_digest(oracle.prove(po2, 0xB2000000 + i))) for i in range(n)]
+        j01 = rec(KIND_JOIN, oracle.hash_pair(oracle.seal_digest(lifts[0]), oracle.seal_digest(lifts[1])))
+        j012 = rec(KIND_JOIN, oracle.hash_pair(oracle.seal_digest(j01), oracle.seal_digest(lifts[2])))
+        assert np.array_equal(root.seal, j012)
+        assert oracle.verify(root.seal) == 0
+
+        # a corrupted stored receipt is caught by the device-side verify_integrity inside the join task
+        job2 = db.create_job(execs, wire.task_type_to_value(wire.ExecutorReq(image=IMAGE, input="input:1", user_id="u")), user_id="u")
+        tasks.poll_work(tasks.Agent(db, store, None, tasks.AgentArgs(task_stream=wire.EXEC_WORK_TYPE)))
+        tasks.poll_work(gpu_agent, max_tasks=2)
+        key = "job:%s:recursion_receipts:0" % job2
+        bad = wire.deserialize_succinct(store.get_bytes(key)); bad.seal[bad.seal.size // 3] ^= 1
+        store.set_bytes(key, wire.serialize_succinct(bad))
+        tasks.poll_work(gpu_agent)
+        assert db.job_state(job2) == "failed"
+        assert "[BENTO-JOIN-003] Failed to verify left receipt integrity: seal does not verify" in db.job_error(job2)
+    finally:
+        srv.close()

@@ -1,0 +1,299 @@
+"""Host logic either side of the proving path, on the CPU with a fake prover: wire formats (workflow-common), taskdb scheduling
+semantics (redis_backend.rs Lua), the task functions (tasks/prove.rs, join.rs, union.rs, resolve.rs, finalize.rs) and the
+agent's dispatch / retry loop (workflow/src/lib.rs:611-799).  The GPU twin with real proofs is tests/test_gpu_tasks.py."""
+import hashlib
+import json
+
+import numpy as np
+import pytest
+
+from boundless_b200 import tasks, wire
+from boundless_b200.prover_server import (KIND_JOIN, KIND_LIFT, KIND_RESOLVE, KIND_UNION, Segment, SegmentReceipt, SuccinctReceipt,
+                                          VerificationError)
+from boundless_b200.taskdb import INIT_TASK, MemoryTaskDb, TaskDbError
+
+IMAGE = "ab" * 32
+
+
+def _seal(tag, *parts):
+    h = hashlib.sha256(repr((tag,) + parts).encode()).digest()
+    return np.frombuffer(h * 4, dtype=np.uint32).copy()
+
+
+class FakeProver:
+    """Deterministic stand-in with the ProverServer method names; a seal whose first word is 0xBAD fails verification."""
+
+    def __init__(self):
+        self.calls = []
+        self.fail_next = {}
+
+    def _maybe_fail(self, what):
+        if self.fail_next.get(what, 0) > 0:
+            self.fail_next[what] -= 1
+            raise RuntimeError("injected %s failure" % what)
+
+    def prove_segment(self, ctx, segment):
+        self._maybe_fail("prove_segment")
+        self.calls.append(("prove_segment", segment.index))
+        return SegmentReceipt(_seal("seg", segment.index, segment.seed, segment.po2), segment.index, segment.po2, list(segment.assumptions))
+
+    def lift(self, r):
+        self.calls.append(("lift", r.index))
+        return SuccinctReceipt(_seal("lift", r.seal.tobytes()), KIND_LIFT, (r.index, r.index), list(r.assumptions))
+
+    def join(self, a, b):
+        self._maybe_fail("join")
+        self.calls.append(("join", a.claim, b.claim))
+        assert a.claim[1] + 1 == b.claim[0], "join of non-adjacent receipts"
+        return SuccinctReceipt(_seal("join", a.seal.tobytes(), b.seal.tobytes()), KIND_JOIN, (a.claim[0], b.claim[1]),
+                               list(a.assumptions) + list(b.assumptions))
+
+    def union(self, a, b):
+        self.calls.append(("union",))
+        return SuccinctReceipt(_seal("union", a.seal.tobytes(), b.seal.tobytes()), KIND_UNION, (0, 0))
+
+    def resolve(self, cond, asm):
+        self.calls.append(("resolve", asm.claim_digest()))
+        gone = asm.claim_digest()
+        assert gone in cond.assumptions
+        return SuccinctReceipt(_seal("resolve", cond.seal.tobytes(), asm.seal.tobytes()), KIND_RESOLVE, tuple(cond.claim),
+                               [x for x in cond.assumptions if x != gone])
+
+    def verify_integrity(self, receipt, slot=0):
+        self.calls.append(("verify",))
+        if int(receipt.seal[0]) == 0xBAD:
+            raise VerificationError(120)
+
+
+# ---- wire ------------------------------------------------------------------------------------------------------------------
+def test_task_type_json_matches_serde():
+    """Externally tagged enums, unit variant as a bare string (workflow-common/src/lib.rs:150-168)."""
+    assert wire.task_type_to_json(wire.ProveReq(3)) == '{"Prove":{"index":3}}'
+    assert wire.task_type_to_json(wire.JoinReq(5, 1, 2)) == '{"Join":{"idx":5,"left":1,"right":2}}'
+    assert wire.task_type_to_json(wire.ResolveReq(100, 50)) == '{"Resolve":{"max_idx":100,"union_max_idx":50}}'
+    assert wire.task_type_to_json(wire.ResolveReq(7)) == '{"Resolve":{"max_idx":7,"union_max_idx":null}}'
+    assert wire.task_type_to_json(wire.Finalize()) == '"Finalize"'
+    assert wire.task_type_to_json(wire.UnionReq(9, 3, 4)) == '{"Union":{"idx":9,"left":3,"right":4}}'
+    for t in (wire.ProveReq(0), wire.JoinReq(2, 0, 1), wire.UnionReq(2, 0, 1), wire.ResolveReq(4, None), wire.Finalize(),
+              wire.SnarkReq("abc", "Groth16"), wire.ExecutorReq("img", "inp", "user", ["a"], False, "None", 5)):
+        assert wire.task_type_from_json(wire.task_type_to_json(t)) == t
+    # the reference's own unit test (workflow-common/src/lib.rs:190-224)
+    r = wire.ResolveReq(max_idx=100, union_max_idx=50)
+    assert r.max_idx == 100 and r.union_max_idx == 50
+    names = [wire.to_job_type_str(t) for t in (wire.ExecutorReq("i", "j", "u"), wire.ProveReq(1), wire.JoinReq(1, 2, 3), wire.ResolveReq(1),
+                                               wire.Finalize(), wire.SnarkReq("r"), wire.KeccakReq([0] * 8, 16, [0] * 8), wire.UnionReq(1, 2, 3))]
+    assert names == ["executor", "prove-lift", "join", "resolve", "finalize", "snark", "keccak", "union"]
+
+
+@pytest.mark.parametrize("bad", ['{"Prove":{}}', '{"Prove":{"index":-1}}', '{"Prove":{"index":1,"x":2}}', '{"Nope":{}}', '"Prove"', "[1]",
+                                 '{"Prove":{"index":1},"Join":{}}', "{", '{"Executor":{"image":"a","input":"b","user_id":"c","compress":"Zip"}}'])
+def test_task_type_rejects_malformed(bad):
+    with pytest.raises(wire.WireError):
+        wire.task_type_from_json(bad)
+
+
+def test_bincode_blobs_roundtrip_and_layout():
+    seg = Segment(index=3, po2=12, seed=0xB2000003)
+    blob = wire.serialize_segment(seg)
+    # bincode 1.x: u64 index, u32 po2, u64 seed, Option tag 0, u64 len 0
+    assert blob == (3).to_bytes(8, "little") + (12).to_bytes(4, "little") + (0xB2000003).to_bytes(8, "little") + b"\x00" + bytes(8)
+    back = wire.deserialize_segment(blob)
+    assert (back.index, back.po2, back.seed, back.trace, back.assumptions) == (3, 12, 0xB2000003, None, [])
+    seg2 = Segment(index=1, po2=9, seed=5, trace=np.arange(7, dtype=np.uint32), assumptions=["ff" * 32])
+    b2 = wire.deserialize_segment(wire.serialize_segment(seg2))
+    assert np.array_equal(b2.trace, seg2.trace) and b2.assumptions == ["ff" * 32]
+    rc = SuccinctReceipt(np.arange(100, dtype=np.uint32), KIND_JOIN, (2, 5), ["aa", "bb"])
+    b3 = wire.deserialize_succinct(wire.serialize_succinct(rc))
+    assert np.array_equal(b3.seal, rc.seal) and (b3.kind, b3.claim, b3.assumptions) == (KIND_JOIN, (2, 5), ["aa", "bb"])
+    roll = wire.serialize_rollup(rc, b"journal-bytes")
+    assert roll[:4] == (1).to_bytes(4, "little")                      # InnerReceipt::Succinct
+    r4, j4 = wire.deserialize_rollup(roll)
+    assert np.array_equal(r4.seal, rc.seal) and j4 == b"journal-bytes"
+    for broken in (blob[:-1], blob + b"\x00", b"", roll[:10]):
+        with pytest.raises(wire.WireError):
+            (wire.deserialize_rollup if broken is roll[:10] else wire.deserialize_segment)(broken)
+    with pytest.raises(wire.WireError):
+        wire.deserialize_rollup((0).to_bytes(4, "little") + roll[4:])
+
+
+# ---- taskdb ----------------------------------------------------------------------------------------------------------------
+def _db():
+    db = MemoryTaskDb()
+    prove = db.create_stream(wire.PROVE_WORK_TYPE, user_id="u")
+    aux = db.create_stream(wire.AUX_WORK_TYPE, user_id="u")
+    execs = db.create_stream(wire.EXEC_WORK_TYPE, user_id="u")
+    return db, prove, aux, execs
+
+
+def test_taskdb_ready_order_and_dependencies():
+    db, prove, aux, execs = _db()
+    job = db.create_job(execs, {"init": 1}, user_id="u")
+    assert db.request_work(wire.EXEC_WORK_TYPE).task_id == INIT_TASK and db.request_work(wire.EXEC_WORK_TYPE) is None
+    db.create_task(job, "0", prove, "a", [], 1, 10)
+    db.create_task(job, "1", prove, "b", [], 1, 10)
+    db.create_task(job, "2", prove, "join", ["0", "1"], 1, 10)          # created before segment 3 => claimed before it
+    db.create_task(job, "3", prove, "c", [], 1, 10)
+    assert db.task_state(job, "2") == "pending" and db.task_field(job, "2", "waiting_on") == 2
+    with pytest.raises(TaskDbError, match="missing prerequisite task: 9"):
+        db.create_task(job, "4", prove, "x", ["9"], 1, 10)
+    with pytest.raises(TaskDbError, match="task already exists: 3"):
+        db.create_task(job, "3", prove, "x", [], 1, 10)
+    t0 = db.request_work(wire.PROVE_WORK_TYPE); t1 = db.request_work(wire.PROVE_WORK_TYPE)
+    assert (t0.task_id, t1.task_id) == ("0", "1")
+    db.update_task_done(job, "0"); assert db.task_field(job, "2", "waiting_on") == 1
+    db.update_task_done(job, "1"); assert db.task_state(job, "2") == "ready"
+    assert db.request_work(wire.PROVE_WORK_TYPE).task_id == "2"           # the join jumps ahead of the later segment
+    assert db.request_work(wire.PROVE_WORK_TYPE).task_id == "3"
+    assert not db.update_task_done(job, "0")                               # already done
+    # a prerequisite that is already done does not block
+    db.create_task(job, "5", prove, "late", ["0"], 0, 10)
+    assert db.task_state(job, "5") == "ready"
+
+
+def test_taskdb_priority_retry_timeout_and_failure():
+    now = [1000.0]
+    db = MemoryTaskDb(clock=lambda: now[0])
+    prove = db.create_stream(wire.PROVE_WORK_TYPE, user_id="u")
+    execs = db.create_stream(wire.EXEC_WORK_TYPE, user_id="u")
+    low = db.create_job(execs, None, user_id="u", priority=2)
+    high = db.create_job(execs, None, user_id="u", priority=0)
+    db.create_task(low, "a", prove, 1, [], 1, 30)
+    db.create_task(high, "b", prove, 2, [], 1, 30)
+    assert db.request_work(wire.PROVE_WORK_TYPE).job_id == high            # priority 0 before priority 2, despite creation order
+    t = db.request_work(wire.PROVE_WORK_TYPE)
+    assert t.job_id == low and db.get_task_retries_running(low, "a") == 0
+    assert db.requeue_tasks() == 0
+    now[0] += 31                                                             # both claims expire
+    assert db.requeue_tasks() == 2 and db.task_state(low, "a") == "ready" and db.task_field(low, "a", "retries") == 1
+    t = db.request_work(wire.PROVE_WORK_TYPE); t = db.request_work(wire.PROVE_WORK_TYPE)
+    assert not db.update_task_retry(low, "a")                                # retries 2 > max 1
+    assert db.task_state(low, "a") == "failed" and db.job_state(low) == "failed" and db.job_error(low) == "retry max hit"
+    # failing a task fails the job and cancels what has not started
+    db.create_task(high, "c", prove, 3, ["b"], 1, 30)
+    db.create_task(high, "d", prove, 4, [], 1, 30)
+    assert db.update_task_failed(high, "b", "boom")
+    assert db.task_state(high, "c") == "cancelled" and db.task_state(high, "d") == "cancelled"
+    assert db.request_work(wire.PROVE_WORK_TYPE) is None
+
+
+# ---- the job, end to end ------------------------------------------------------------------------------------------------------
+def _run_job(n_segments, prover=None, assumptions=(), args=None):
+    db, prove, aux, execs = _db()
+    store = tasks.MemoryHotStore()
+    prover = prover or FakeProver()
+    store.set_bytes("input:1", json.dumps({"segments": n_segments, "po2": 10}).encode())
+    req = wire.ExecutorReq(image=IMAGE, input="input:1", user_id="u", assumptions=list(assumptions))
+    job = db.create_job(execs, wire.task_type_to_value(req), user_id="u")
+    exec_agent = tasks.Agent(db, store, None, tasks.AgentArgs(task_stream=wire.EXEC_WORK_TYPE, segment_po2=10))
+    gpu_agent = tasks.Agent(db, store, prover, args or tasks.AgentArgs(task_stream=wire.PROVE_WORK_TYPE))
+    aux_agent = tasks.Agent(db, store, prover, tasks.AgentArgs(task_stream=wire.AUX_WORK_TYPE))
+    return db, store, job, prover, exec_agent, gpu_agent, aux_agent
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 13])
+def test_job_reduces_to_one_verified_receipt(n):
+    db, store, job, prover, exec_agent, gpu_agent, aux_agent = _run_job(n)
+    assert tasks.poll_work(exec_agent) == 1
+    assert db.task_field(job, INIT_TASK, "output")["segments"] == n
+    assert sum(1 for k in store.kv if ":segments:" in k) == n
+    assert tasks.poll_work(aux_agent) == 0                                   # finalize is still pending
+    claimed = tasks.poll_work(gpu_agent)
+    assert claimed == n + (n - 1) + 1                                        # proves, joins, resolve
+    assert tasks.poll_work(aux_agent) == 1 and db.job_state(job) == "done"
+    # every intermediate blob was cleaned up after its consumer was marked done; the final receipt is in shared storage
+    assert not [k for k in store.kv if k.startswith("job:")], sorted(store.kv)
+    (key, blob), = store.assets.items()
+    assert key == "receipts/stark/%s.bincode" % job
+    root, journal = wire.deserialize_rollup(blob)
+    assert root.claim == (0, n - 1) and json.loads(journal) == {"segments": n}
+    # prove -> verify -> lift -> verify per segment; verify, verify, join, verify per join
+    assert prover.calls.count(("verify",)) == 2 * n + 3 * (n - 1) + 1
+    # depth-first reduction: a join runs as soon as both inputs exist, before later segments (planner/mod.rs:100-113)
+    order = [c for c in prover.calls if c[0] in ("prove_segment", "join")]
+    if n >= 3:
+        assert order[:3] == [("prove_segment", 0), ("prove_segment", 1), ("join", (0, 0), (1, 1))]
+
+
+def test_two_gpu_agents_share_the_queue():
+    """compose.yml:113: one agent per GPU pulling from the same stream; any interleaving must give the same root."""
+    db, store, job, prover, exec_agent, a0, aux_agent = _run_job(9)
+    a1 = tasks.Agent(db, store, prover, tasks.AgentArgs(task_stream=wire.PROVE_WORK_TYPE))
+    tasks.poll_work(exec_agent)
+    turn = 0
+    while tasks.poll_work((a0, a1)[turn % 2], max_tasks=1 + turn % 3):
+        turn += 1
+    tasks.poll_work(aux_agent)
+    assert db.job_state(job) == "done" and a0.processed and a1.processed
+    root, _ = wire.deserialize_rollup(next(iter(store.assets.values())))
+    db2, store2, job2, _, e2, g2, x2 = _run_job(9)
+    tasks.poll_work(e2); tasks.poll_work(g2); tasks.poll_work(x2)
+    root2, _ = wire.deserialize_rollup(next(iter(store2.assets.values())))
+    assert np.array_equal(root.seal, root2.seal)
+
+
+def test_assumptions_are_resolved_before_finalize():
+    fp = FakeProver()
+    asm = SuccinctReceipt(_seal("assumption"), KIND_LIFT, (0, 0))
+    claim = asm.claim_digest()
+    db, store, job, prover, exec_agent, gpu_agent, aux_agent = _run_job(3, fp, assumptions=[claim])
+    store.set_bytes("job:%s:receipts:%s" % (job, claim), wire.serialize_succinct(asm))
+    tasks.poll_work(exec_agent); tasks.poll_work(gpu_agent)
+    assert db.task_field(job, "resolve", "output") == 1 and ("resolve", claim) in fp.calls
+    assert db.task_field(job, "resolve", "timeout_secs") == tasks.AgentArgs().resolve_timeout * 1
+    tasks.poll_work(aux_agent)
+    assert db.job_state(job) == "done"
+    root, _ = wire.deserialize_rollup(next(iter(store.assets.values())))
+    assert root.kind == KIND_RESOLVE and root.assumptions == []
+    # a missing corroborating receipt fails the resolve task with the reference's context chain
+    db, store, job, prover, exec_agent, gpu_agent, aux_agent = _run_job(2, FakeProver(), assumptions=[claim])
+    tasks.poll_work(exec_agent); tasks.poll_work(gpu_agent)
+    assert db.job_state(job) == "failed"
+    assert db.job_error(job).startswith("retry max hit: [BENTO-WF-123] Resolve failed: corroborating receipt not found: key job:")
+
+
+def test_failures_retry_then_fail_with_truncated_error():
+    fp = FakeProver(); fp.fail_next["join"] = 1                             # one transient failure: retried, job completes
+    db, store, job, prover, exec_agent, gpu_agent, aux_agent = _run_job(2, fp)
+    tasks.poll_work(exec_agent); tasks.poll_work(gpu_agent); tasks.poll_work(aux_agent)
+    assert db.job_state(job) == "done" and db.task_field(job, "2", "retries") == 1
+    assert "job:%s:recursion_receipts:0" % job not in store.kv              # inputs survived the failed attempt, deleted after success
+    fp = FakeProver(); fp.fail_next["prove_segment"] = 99                   # permanent failure
+    db, store, job, prover, exec_agent, gpu_agent, aux_agent = _run_job(3, fp)
+    tasks.poll_work(exec_agent); tasks.poll_work(gpu_agent)
+    assert db.job_state(job) == "failed" and db.task_field(job, "0", "retries") == 3
+    assert db.job_error(job) == "retry max hit: [BENTO-WF-115] Prove failed: injected prove_segment failure"
+    assert db.task_state(job, "finalize") == "cancelled" and "job:%s:segments:0" % job in store.kv
+    # max_retries == 0: fail at once, message truncated to 1024 characters
+    fp = FakeProver(); fp.fail_next["prove_segment"] = 1
+    db, store, job, prover, exec_agent, gpu_agent, aux_agent = _run_job(1, fp, args=tasks.AgentArgs(prove_retries=0))
+    exec_agent.args.prove_retries = 0
+    store.set_bytes("input:1", json.dumps({"segments": 1, "po2": 10}).encode())
+    tasks.poll_work(exec_agent)
+    fp._maybe_fail = lambda what: (_ for _ in ()).throw(RuntimeError("x" * 5000))
+    tasks.poll_work(gpu_agent)
+    assert db.job_state(job) == "failed" and len(db.job_error(job)) == 1024
+
+
+def test_bad_receipts_and_blobs_are_caught():
+    class Forger(FakeProver):
+        def lift(self, r):
+            out = super().lift(r); out.seal[0] = 0xBAD; return out
+    db, store, job, prover, exec_agent, gpu_agent, aux_agent = _run_job(1, Forger())
+    tasks.poll_work(exec_agent); tasks.poll_work(gpu_agent)
+    assert "[BENTO-PROVE-010] Failed to verify lift receipt integrity: seal does not verify (check 120 failed)" in db.job_error(job)
+    # corrupt stored receipt -> join reports which side failed to deserialize
+    db, store, job, prover, exec_agent, gpu_agent, aux_agent = _run_job(2)
+    tasks.poll_work(exec_agent); tasks.poll_work(gpu_agent, max_tasks=2)
+    store.set_bytes("job:%s:recursion_receipts:1" % job, b"\x01\x02")
+    tasks.poll_work(gpu_agent)
+    assert "[BENTO-WF-119] Join failed: [BENTO-JOIN-002] Failed to deserialize right receipt" in db.job_error(job)
+    # an agent without a prover cannot take GPU work; an unknown task_def is "Invalid task_def"
+    db, store, job, prover, exec_agent, gpu_agent, aux_agent = _run_job(1)
+    tasks.poll_work(exec_agent)
+    gpu_agent.prover = None
+    tasks.poll_work(gpu_agent)
+    assert "[BENTO-PROVE-002] Missing prover from prove task" in db.job_error(job)
+    db, prove, aux, execs = _db()
+    job = db.create_job(execs, {"Bogus": {}}, user_id="u")
+    tasks.poll_work(tasks.Agent(db, tasks.MemoryHotStore(), None, tasks.AgentArgs(task_stream=wire.EXEC_WORK_TYPE)))
+    assert db.job_error(job).startswith("Invalid task_def: %s:init: unknown variant `Bogus`" % job)
