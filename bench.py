@@ -99,7 +99,7 @@ def reference_arm(args):
     scale = 1 << (PO2 - sample_po2)
     sps = args.steps / (dt * scale)
     sample = "%d x one 2^%d-row segment (same widths/protocol), time scaled x%d to 2^20 rows" % (args.steps, sample_po2, scale)
-    out = {"impl": "reference", "metric": "segments_per_sec", "value": sps, "unit": "segments/s", "n_gpus": 0, "steps": args.steps,
+    out = {"impl": "reference", "metric": "segments_per_sec", "value": sps, "unit": "segments/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 * scale, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
            "proved_mcycles_per_sec": sps * CYCLES_PER_SEGMENT / 1e6,

@@ -13,13 +13,13 @@ OBJ = os.path.join(HERE, "_obj")
 SO = os.path.join(HERE, "libb200zkp.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-SOURCES = ["ntt.cu", "hash.cu", "stark.cu", "halops.cu", "verify.cu", "tables.cpp", "prover.cpp", "capi.cpp", "planner.cpp"]
+SOURCES = ["ntt.cu", "hash.cu", "stark.cu", "halops.cu", "verify.cu", "compat.cu", "tables.cpp", "prover.cpp", "capi.cpp", "planner.cpp"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-ccbin", HOSTCXX,
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-I", CSRC, "-I", os.path.join(HERE, "..", "include")]
 
 
 def _deps():
-    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "b200zkp.h")]
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", h) for h in ("b200zkp.h", "b200_risc0_sys_compat.h")]
 
 
 def _stale(target, deps):

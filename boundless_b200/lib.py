@@ -85,6 +85,25 @@ SYMBOLS = {
     "b200_planner_next_task": (C.c_int, [_vp, C.POINTER(Task)]),
 }
 
+
+
+class SpparkError(C.Structure):
+    """sppark::Error returned BY VALUE by the risc0-sys-compatible exports (include/b200_risc0_sys_compat.h)."""
+    _fields_ = [("code", C.c_int32), ("message", C.c_void_p)]      # message: malloc()ed, freed by the caller
+
+
+# include/b200_risc0_sys_compat.h: the original risc0-sys / sppark symbol names
+COMPAT_SYMBOLS = {
+    "sppark_init": (SpparkError, []),
+    "sppark_batch_iNTT": (SpparkError, [_vp, _u32, _u32]),
+    "sppark_batch_NTT": (SpparkError, [_vp, _u32, _u32]),
+    "sppark_batch_zk_shift": (SpparkError, [_vp, _u32, _u32]),
+    "sppark_batch_expand": (SpparkError, [_vp, _vp, _u32, _u32, _u32]),
+    "sppark_poseidon2_rows": (SpparkError, [_vp, _vp, _u32, _u32]),
+    "sppark_poseidon2_fold": (SpparkError, [_vp, _vp, _sz]),
+    "supra_poly_divide": (SpparkError, [_vp, _sz, _vp, _vp]),
+}
+
 _lib = None
 
 
@@ -95,7 +114,7 @@ def load():
         if not os.path.exists(SO_PATH):
             raise B200Error("libb200zkp.so not built: run `python -m boundless_b200.build` (needs nvcc; there is no CPU path)")
         L = C.CDLL(SO_PATH)
-        for name, (res, args) in SYMBOLS.items():
+        for name, (res, args) in list(SYMBOLS.items()) + list(COMPAT_SYMBOLS.items()):
             f = getattr(L, name)           # AttributeError if the ABI and the header drift apart
             f.restype = res
             f.argtypes = args
@@ -106,6 +125,16 @@ def load():
 def check(err):
     if err is not None:
         raise B200Error(err.decode() if isinstance(err, bytes) else str(err))
+
+
+def check_sppark(err):
+    """Turn a by-value sppark::Error into an exception, freeing its message the way the Rust Drop does."""
+    if err.code == 0 and not err.message:
+        return
+    msg = C.string_at(err.message).decode() if err.message else "sppark error %d" % err.code
+    if err.message:
+        C.CDLL(None).free(C.c_void_p(err.message))
+    raise B200Error("%s (code %d)" % (msg, err.code))
 
 
 def require_gpu(device=0):

@@ -1,5 +1,6 @@
 """Launch each hot kernel a few times at the BASELINE shapes (16 columns x 2^20 rows) for ncu captures.
-usage: python tools/prof_kernels.py [what...]   what in {ntt, rows, fold}"""
+usage: python tools/prof_kernels.py [what...]   what in {ntt, rows, rows208, fold, hal}
+hal = K6 fri_fold, K7 batch_evaluate_any, K8 mix_poly_coeffs / eltwise_sum_extelem / poly_divide at the segment's sizes."""
 import ctypes as C
 import os
 import sys
@@ -38,5 +39,28 @@ if "rows208" in what:      # the bench's roofline kernel: K4 on the data group (
 if "fold" in what:
     nodes = torch.randint(0, P, (2 * (1 << 22) * 8,), dtype=torch.int32, device="cuda")
     assert L.b200_poseidon2_fold(p(nodes), p(nodes[(1 << 22) * 8:]), 1 << 21, None) is None
+    torch.cuda.synchronize()
+if "hal" in what:
+    N = 1 << 20
+    rnd = lambda k: torch.randint(0, P, (k,), dtype=torch.int32, device="cuda")
+    # K6: first FRI round, 4 planes x 2^20 -> 4 planes x 2^16
+    fin, fout, mix = rnd(4 * N), rnd(4 * (N // 16)), rnd(4)
+    assert L.b200_fri_fold(p(fout), p(fin), N, p(mix), None) is None
+    # K7: 64 coefficient columns x 2^20 at one Fp4 point
+    cols = 64
+    co, x, ev = rnd(cols * N), rnd(4), rnd(cols * 4)
+    scr = torch.empty(L.b200_evaluate_scratch_words(20, cols), dtype=torch.int32, device="cuda")
+    assert L.b200_batch_evaluate_any(p(ev), p(co), 20, cols, p(x), p(scr), None) is None
+    # K8a: 64 columns mixed into 3 combos of 2^20 ExtElems
+    comb = torch.tensor([i % 3 for i in range(cols)], dtype=torch.int32, device="cuda")
+    acc = torch.zeros(3 * N * 4, dtype=torch.int32, device="cuda")
+    assert L.b200_mix_poly_coeffs(p(acc), p(mix), p(x), p(co), p(comb), cols, N, 3, None) is None
+    # K8b: sum of the 3 combos -> 4 planes
+    planes = torch.empty(4 * N, dtype=torch.int32, device="cuda")
+    assert L.b200_eltwise_sum_extelem(p(planes), p(acc), N, 3, None) is None
+    # K8c: synthetic division of a 2^20-coefficient ExtElem polynomial
+    rem = torch.empty(4, dtype=torch.int32, device="cuda")
+    dscr = torch.empty(L.b200_poly_divide_scratch_words(N), dtype=torch.int32, device="cuda")
+    assert L.b200_poly_divide(p(acc), N, p(rem), p(x), p(dscr), None) is None
     torch.cuda.synchronize()
 print("done")
