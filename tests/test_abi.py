@@ -84,3 +84,32 @@ def test_rust_sys_binding_declares_the_same_symbols():
     src = open(os.path.join(ROOT, "bindings", "rust", "b200zkp-sys", "src", "lib.rs")).read()
     rust = sorted(set(re.findall(r"pub fn (b200_[a-z0-9_]+)\s*\(", src)))
     assert rust == header_functions()
+
+
+def compat_header_functions():
+    txt = open(os.path.join(ROOT, "include", "b200_risc0_sys_compat.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:sppark|supra)_[A-Za-z0-9_]+)\s*\(", txt)))
+
+
+def test_risc0_sys_compat_symbols_are_exported(b200lib):
+    """include/b200_risc0_sys_compat.h: the original risc0-sys / sppark names, so the Rust side links unchanged."""
+    from boundless_b200 import lib
+    names = compat_header_functions()
+    assert names == sorted(lib.COMPAT_SYMBOLS) and len(names) == 8
+    for n in names:
+        assert hasattr(b200lib, n), "missing export " + n
+
+
+def test_risc0_sys_compat_fails_loudly_without_gpu(b200lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from boundless_b200 import lib
+    for call in (lambda: b200lib.sppark_init(), lambda: b200lib.sppark_batch_iNTT(None, 10, 1),
+                 lambda: b200lib.sppark_batch_expand(None, None, 10, 2, 1), lambda: b200lib.sppark_poseidon2_rows(None, None, 4, 4),
+                 lambda: b200lib.supra_poly_divide(None, 4, None, None)):
+        err = call()
+        assert err.code != 0 and err.message
+        with pytest.raises(lib.B200Error, match="no CUDA device"):
+            lib.check_sppark(err)        # also frees the malloc()ed message, like sppark::Error's Drop
