@@ -30,7 +30,7 @@ __device__ __forceinline__ uint32_t addmin(uint32_t x, uint32_t y, uint32_t z) {
 #define B200_ADD_V 0
 #endif
 #ifndef B200_REDC_V
-#define B200_REDC_V 0
+#define B200_REDC_V 3      // measured: +1 % on the Poseidon2 permutation over variant 0 (profiles/microbench_zadd_r01.txt)
 #endif
 __device__ __forceinline__ uint32_t fp_add(uint32_t a, uint32_t b) {
 #if B200_ADD_V == 0
@@ -49,6 +49,18 @@ __device__ __forceinline__ uint32_t fp_sub(uint32_t a, uint32_t b) {
     return addmin(d, 0u - P, d);            // min(d - p, d)
 #endif
 }
+// A runtime zero the compiler cannot see through (%ctaid.z of a 1-deep grid; a uniform register, read once per thread): adding it
+// makes a sum a THREE-input add, which only IADD3 (ALU pipe) can encode -- ptxas cannot turn it into IMAD.IADD (multiplier pipe).
+// Used to steer chosen adds off the multiplier pipe in the multiplier-bound kernels (B200_P2_Z in poseidon2.cuh).
+__device__ __forceinline__ uint32_t zreg() { uint32_t z; asm("mov.u32 %0, %%ctaid.z;" : "=r"(z)); return z; }
+__device__ __forceinline__ uint32_t fp_add_z(uint32_t a, uint32_t b) {
+    uint32_t s = a + b + zreg();
+    return addmin(s, 0u - P, s);
+}
+__device__ __forceinline__ uint32_t fp_sub_z(uint32_t a, uint32_t b) {
+    uint32_t d = a - b + zreg();
+    return addmin(d, P, d);
+}
 __device__ __forceinline__ uint32_t fp_neg(uint32_t a) { return a ? P - a : 0u; }
 __device__ __forceinline__ uint32_t fp_dbl(uint32_t a) { return fp_add(a, a); }
 
@@ -64,6 +76,11 @@ __device__ __forceinline__ uint32_t fp_redc(uint32_t hi, uint32_t lo) {
     uint64_t o2 = (uint64_t)m * P + (((uint64_t)hi << 32) | lo);   // IMAD.HI(m, P, lo) + hi; low word cancels
     uint32_t r = (uint32_t)(o2 >> 32);      // (T + m*p) / 2^32 in [0, 2p)
     return addmin(r, 0u - P, r);            // min(r - p, r)
+#elif B200_REDC_V == 3
+    uint32_t m = lo * PINV;
+    uint32_t t = __umulhi(m, P);
+    uint32_t r = hi - t + zreg();           // three-input form: stays an IADD3 (ALU pipe)
+    return addmin(r, P, r);
 #else
     uint32_t m = lo + ((lo + (lo << 4)) << 27);   // lo * 0x88000001 with two LEAs (ALU pipe) instead of an IMAD
     uint32_t t = __umulhi(m, P);

@@ -594,6 +594,153 @@ __global__ void __launch_bounds__(512) k_ntt_strided_pf(uint32_t* __restrict__ d
     }
 }
 
+// =========================================================================================================
+// Radix-32 register passes for the 1024-row strided tile (the hot shape: both 2^20 and 2^22 transforms split as 2^10 x rest).
+// A 10-level transform is TWO register stages of 5 levels with ONE exchange through shared memory:
+//   contiguous stage: a thread owns rows 32b..32b+31 of one column; its twiddles w_32^k are compile-time constants
+//                     (immediate operands, and the 31 of 80 multiplications by w^0 = 1 are not emitted at all);
+//   strided stage:    a thread owns rows t, t+32, ..., t+992; its 31 distinct twiddles come from the TMA-staged table.
+// 256 threads = 8 columns x 32 row groups; one padding row per 32 rows makes both access patterns bank-conflict free
+// (a warp touches 8 consecutive words at 4 row offsets that land 8 banks apart).  Against the radix-16 kernel
+// (k_ntt_strided_pf: 4+4+2 levels) a tile makes one shared-memory round trip and one block barrier less and issues
+// about a third fewer instructions.
+// =========================================================================================================
+__host__ __device__ constexpr uint32_t c_mulmod(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a * b % P); }
+__host__ __device__ constexpr uint32_t c_powmod(uint32_t a, uint64_t e) {
+    uint32_t r = 1;
+    while (e) { if (e & 1) r = c_mulmod(r, a); a = c_mulmod(a, a); e >>= 1; }
+    return r;
+}
+constexpr uint32_t W32_FWD = c_powmod(137u, 1ull << 22);      // ROU_FWD[5] = 137^(2^(27-5)), plain value
+constexpr uint32_t W32_INV = c_powmod(W32_FWD, 31);
+static_assert(c_powmod(W32_FWD, 16) == P - 1 && c_mulmod(W32_FWD, W32_INV) == 1, "w_32");
+// w_32^k (k < 16) of the forward / inverse root as a Shoup pair, usable as immediates after unrolling
+template <bool INV>
+__host__ __device__ constexpr tw_t w32_pair(int k) {
+    const uint32_t w = c_powmod(INV ? W32_INV : W32_FWD, (uint64_t)k);
+    return tw_t{w, (uint32_t)(((uint64_t)w << 32) / P)};
+}
+
+// five butterfly levels on x[0..32): x[j] is the element at position o + j*q of its block.
+// CONST: q = 1 (levels 1..5, twiddle of pair index i at sub-level m is w_32^(i * 2^(5-m)));
+// otherwise q = 32 (levels 6..10, twiddle tws[(16 << m) + t + 32*i] from the compact per-level table).
+template <bool DIF, bool CONST>
+__device__ __forceinline__ void radix32_levels(uint32_t (&x)[32], const tw_t* __restrict__ tws, uint32_t t) {
+#pragma unroll
+    for (int mm = 0; mm < 5; mm++) {
+        const int m = DIF ? 5 - mm : mm + 1;        // sub-level 1..5; DIF runs from the widest butterflies down
+        const int half = 1 << (m - 1);
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            if ((j & half) == 0) {
+                const int i = j & (half - 1);
+                const bool one = CONST && i == 0;
+                tw_t w;
+                if (CONST) w = w32_pair<DIF>(i << (5 - m)); else w = tws[(16u << m) + t + 32u * i];
+                const uint32_t a = x[j], b = x[j + half];
+                if (DIF) {
+                    x[j] = fp_add(a, b);
+                    x[j + half] = one ? fp_sub(a, b) : mul_tw(a - b + P, w);     // a - b + p in (0, 2p): mul_tw takes any u32
+                } else {
+                    const uint32_t tt = one ? b : mul_tw(b, w);
+                    x[j] = fp_add(a, tt);
+                    x[j + half] = fp_sub(a, tt);
+                }
+            }
+        }
+    }
+}
+
+// LGRS >= 0: row_stride == 2^LGRS is a compile-time constant, so every global address of a tile is base + immediate.
+template <bool DIF, int MINB, int LGRS>
+__global__ void __launch_bounds__(256, MINB) k_ntt_strided_r32(uint32_t* __restrict__ data, uint32_t row_stride_rt, uint32_t tiles_per_poly,
+                                                                uint32_t num_tiles, size_t poly_stride, const tw_t* __restrict__ tw_g,
+                                                                const tw_t* __restrict__ pow_g, uint32_t lg_m) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    constexpr uint32_t L = 1024, TILE = (L + (L >> 5)) * 8;
+    const uint32_t tid = threadIdx.x;
+    const size_t row_stride = LGRS >= 0 ? ((size_t)1 << (LGRS >= 0 ? LGRS : 0)) : (size_t)row_stride_rt;
+    const uint32_t h = (lg_m + 1) / 2, lmask = (1u << h) - 1, mmask = (1u << lg_m) - 1;
+    const tw_t* plo = pow_g; const tw_t* phi = pow_g + (1u << h);
+    tw_t* tw_s = reinterpret_cast<tw_t*>(smem + 2 * TILE);
+    __shared__ __align__(8) uint64_t tw_bar;
+    if (tid == 0) mbar_init(&tw_bar, 1);
+    __syncthreads();
+    if (tid == 0) tma_load_1d(tw_s, tw_g, L * 8, &tw_bar);
+    // chunk i of thread tid: row (tid >> 1) + 128 i, half (tid & 1): 128 rows = 132 padded rows apart in shared memory
+    const uint32_t ld_r = tid >> 1, ld_soff = (ld_r + (ld_r >> 5)) * 8 + (tid & 1) * 4;
+    auto issue_load = [&](uint32_t tile, uint32_t* buf) {
+        const uint32_t* g = data + (size_t)(tile / tiles_per_poly) * poly_stride + (size_t)(tile % tiles_per_poly) * 8 + ld_r * row_stride + (tid & 1) * 4;
+#pragma unroll
+        for (int i = 0; i < 8; i++) cp_async16(buf + ld_soff + i * 132 * 8, g + (size_t)(128 * i) * row_stride);
+        cp_async_commit();
+    };
+    const uint32_t c = tid & 7u, grp = tid >> 3;                 // column of the tile, row group 0..31
+    // contiguous stage: rows 32*grp + j  -> word (33*grp + j)*8 + c;   strided stage: rows grp + 32*k -> word (grp + 33*k)*8 + c
+    const uint32_t off_contig = (33u * grp) * 8u + c, off_strided = grp * 8u + c;
+    uint32_t cur = 0, tile = blockIdx.x;
+    if (tile < num_tiles) issue_load(tile, smem);
+    mbar_wait(&tw_bar, 0);
+    for (; tile < num_tiles; tile += gridDim.x) {
+        uint32_t* buf = smem + cur * TILE;
+        const uint32_t next = tile + gridDim.x;
+        if (next < num_tiles) { issue_load(next, smem + (cur ^ 1) * TILE); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        uint32_t* g = data + (size_t)(tile / tiles_per_poly) * poly_stride + (size_t)(tile % tiles_per_poly) * 8 + c +
+                      (size_t)(DIF ? 32u * grp : grp) * row_stride;      // first row this thread stores
+        uint32_t x[32];
+        if constexpr (!DIF) {
+            // levels 1..5 on 32 consecutive rows (constant twiddles), back to shared memory
+            uint32_t* p1 = buf + off_contig;
+#pragma unroll
+            for (int j = 0; j < 32; j++) x[j] = p1[j * 8];
+            radix32_levels<false, true>(x, nullptr, 0u);
+#pragma unroll
+            for (int j = 0; j < 32; j++) p1[j * 8] = x[j];
+            __syncthreads();
+            // levels 6..10 on rows grp + 32k, straight to global memory
+            const uint32_t* p2 = buf + off_strided;
+#pragma unroll
+            for (int k = 0; k < 32; k++) x[k] = p2[k * 33 * 8];
+            radix32_levels<false, false>(x, tw_s, grp);
+#pragma unroll
+            for (int k = 0; k < 32; k++) g[(size_t)(32 * k) * row_stride] = x[k];
+        } else {
+            // levels 10..6 on rows grp + 32k, back to shared memory
+            uint32_t* p2 = buf + off_strided;
+#pragma unroll
+            for (int k = 0; k < 32; k++) x[k] = p2[k * 33 * 8];
+            radix32_levels<true, false>(x, tw_s, grp);
+#pragma unroll
+            for (int k = 0; k < 32; k++) p2[k * 33 * 8] = x[k];
+            __syncthreads();
+            // levels 5..1 on 32 consecutive rows (constant twiddles), inter-pass twiddle, straight to global memory
+            const uint32_t* p1 = buf + off_contig;
+#pragma unroll
+            for (int j = 0; j < 32; j++) x[j] = p1[j * 8];
+            radix32_levels<true, true>(x, nullptr, 0u);
+            // exponent col * bitrev10(32 grp + j) = col * bitrev5(grp) + (col << 5) * bitrev5(j): two per-tile values and an immediate
+            const uint32_t col = (tile % tiles_per_poly) * 8 + c;
+            const uint32_t ea = col * bitrev(grp, 5), eb = col << 5;
+            if (pow_g) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    constexpr uint32_t BR5[32] = {0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30,
+                                                  1, 17, 9, 25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31};
+                    const uint32_t e = (ea + eb * BR5[j]) & mmask;
+                    g[(size_t)j * row_stride] = pow_apply(x[j], __ldg(plo + (e & lmask)), __ldg(phi + (e >> h)));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) g[(size_t)j * row_stride] = x[j];
+            }
+        }
+        __syncthreads();       // every thread is done with buf before the next iteration's prefetch overwrites it
+        cur ^= 1;
+    }
+}
+
 // forward pass 1: rows of Lin = Lc/4 bit-reversed coefficients -> Lc values (levels 3..LOGLC of the size-Lc DIT), times
 // w_M^(k * d1).  One work item of the head = 4 coefficients -> 16 consecutive positions (levels 3 and 4 in registers).
 template <int LOGLC, int LGE>
@@ -806,6 +953,19 @@ static cudaError_t run_strided(const DeviceTables* T, uint32_t* d, uint32_t logL
         const uint32_t tpp = ncols / 8, num_tiles = tpp * count;
         uint32_t per_sm = (uint32_t)(226 * 1024 / (sm + 1024)); if (per_sm > 4) per_sm = 4; if (per_sm < 1) per_sm = 1;
         uint32_t grid = (uint32_t)T->sm_count * per_sm; if (grid > num_tiles) grid = num_tiles;
+        if (logL == 10 && env_int("B200_NTT_R32", 1)) {
+            // radix-32 register kernel: 256 threads, 2 x 1056 x 8 words of tile + the 1024-entry stage table
+            const size_t sm32 = (size_t)2 * (1024 + 32) * 8 * 4 + 1024 * 8;
+            const int nb = env_int("B200_NTT_R32_MINB", DIF ? 2 : 3) == 3 ? 3 : 2;      // measured best per direction (tools/time_ntt2.py)
+            uint32_t g32 = (uint32_t)T->sm_count * (uint32_t)nb; if (g32 > num_tiles) g32 = num_tiles;
+            const int lgrs = row_stride == 1024 ? 10 : (row_stride == 4096 ? 12 : -1);
+#define B200_R32_LAUNCH(NB, RS) { auto kp = k_ntt_strided_r32<DIF, NB, RS>; \
+                cudaError_t e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm32); if (e != cudaSuccess) return e; \
+                B200_LAUNCH(kp)<<<g32, 256, sm32, s>>>(d, row_stride, tpp, num_tiles, poly_stride, twt, pow_g, lg_m); return cudaGetLastError(); }
+            if (nb == 3) { if (lgrs == 10) B200_R32_LAUNCH(3, 10) else if (lgrs == 12) B200_R32_LAUNCH(3, 12) else B200_R32_LAUNCH(3, -1) }
+            else { if (lgrs == 10) B200_R32_LAUNCH(2, 10) else if (lgrs == 12) B200_R32_LAUNCH(2, 12) else B200_R32_LAUNCH(2, -1) }
+#undef B200_R32_LAUNCH
+        }
 #define B200_STRIDED_PF_CASE(LL) case LL: { auto kp = k_ntt_strided_pf<LL, DIF>; \
             cudaError_t e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
             B200_LAUNCH(kp)<<<grid, env_int("B200_NTT_THREADS", 512), sm, s>>>(d, row_stride, tpp, num_tiles, poly_stride, twt, pow_g, lg_m); return cudaGetLastError(); }

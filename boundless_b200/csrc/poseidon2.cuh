@@ -35,10 +35,18 @@ __device__ __forceinline__ uint32_t fp_add_alu(uint32_t a, uint32_t b) {
     uint32_t s = addmin(a, b, 0xffffffffu);
     return addmin(s, 0u - P, s);
 }
-#define P2_ADD_M4(a, b)  ((B200_P2_V & 1) ? fp_add_alu(a, b) : fp_add(a, b))
-#define P2_ADD_SUM(a, b) ((B200_P2_V & 2) ? fp_add_alu(a, b) : fp_add(a, b))
-#define P2_ADD_FIN(a, b) ((B200_P2_V & 4) ? fp_add_alu(a, b) : fp_add(a, b))
-#define P2_ADD_INT(a, b) ((B200_P2_V & 8) ? fp_add_alu(a, b) : fp_add(a, b))
+// B200_P2_Z: bitmask of add classes written as three-input adds (fp_add_z: IADD3 only, never IMAD.IADD):
+// 1 M4 blocks, 2 column sums, 4 final adds of the external layer, 8 sum tree of the internal layer, 16 round-constant adds,
+// 32 the "+ s" of the internal layer.
+#ifndef B200_P2_Z
+#define B200_P2_Z 0
+#endif
+#define P2_ADD_M4(a, b)  ((B200_P2_Z & 1) ? fp_add_z(a, b) : (B200_P2_V & 1) ? fp_add_alu(a, b) : fp_add(a, b))
+#define P2_ADD_SUM(a, b) ((B200_P2_Z & 2) ? fp_add_z(a, b) : (B200_P2_V & 2) ? fp_add_alu(a, b) : fp_add(a, b))
+#define P2_ADD_FIN(a, b) ((B200_P2_Z & 4) ? fp_add_z(a, b) : (B200_P2_V & 4) ? fp_add_alu(a, b) : fp_add(a, b))
+#define P2_ADD_INT(a, b) ((B200_P2_Z & 8) ? fp_add_z(a, b) : (B200_P2_V & 8) ? fp_add_alu(a, b) : fp_add(a, b))
+#define P2_ADD_RC(a, b)  ((B200_P2_Z & 16) ? fp_add_z(a, b) : fp_add(a, b))
+#define P2_ADD_IS(a, b)  ((B200_P2_Z & 32) ? fp_add_z(a, b) : fp_add(a, b))
 
 __device__ __forceinline__ uint32_t p2_sbox(uint32_t x) {
     uint32_t x2 = fp_mul(x, x);
@@ -61,9 +69,9 @@ __device__ __forceinline__ void p2_m_ext(uint32_t (&c)[24]) {
         c[4 * k + 2] = P2_ADD_M4(t2, t4);
         c[4 * k + 3] = t4;
     }
-    uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    uint32_t s0 = c[0], s1 = c[1], s2 = c[2], s3 = c[3];
 #pragma unroll
-    for (int k = 0; k < 6; k++) {
+    for (int k = 1; k < 6; k++) {
         s0 = P2_ADD_SUM(s0, c[4 * k]); s1 = P2_ADD_SUM(s1, c[4 * k + 1]);
         s2 = P2_ADD_SUM(s2, c[4 * k + 2]); s3 = P2_ADD_SUM(s3, c[4 * k + 3]);
     }
@@ -91,7 +99,7 @@ __device__ __forceinline__ void p2_m_int(uint32_t (&c)[24]) {
         const uint32_t q = __umulhi(c[i], c_diag_shoup[i]);
         uint32_t r = c[i] * c_diag_plain[i] - q * P;
         r = addmin(r, 0u - P, r);
-        c[i] = fp_add(r, s);
+        c[i] = P2_ADD_IS(r, s);
     }
     return;
 #endif
@@ -110,18 +118,18 @@ __device__ __forceinline__ void p2_permute(uint32_t (&c)[24]) {
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
 #pragma unroll
-        for (int i = 0; i < 24; i++) c[i] = p2_sbox(fp_add(c[i], c_rc[24 * r + i]));
+        for (int i = 0; i < 24; i++) c[i] = p2_sbox(P2_ADD_RC(c[i], c_rc[24 * r + i]));
         p2_m_ext(c);
     }
 #pragma unroll 1
     for (int r = 0; r < 21; r++) {
-        c[0] = p2_sbox(fp_add(c[0], c_rc[96 + r]));
+        c[0] = p2_sbox(P2_ADD_RC(c[0], c_rc[96 + r]));
         p2_m_int(c);
     }
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
 #pragma unroll
-        for (int i = 0; i < 24; i++) c[i] = p2_sbox(fp_add(c[i], c_rc[117 + 24 * r + i]));
+        for (int i = 0; i < 24; i++) c[i] = p2_sbox(P2_ADD_RC(c[i], c_rc[117 + 24 * r + i]));
         p2_m_ext(c);
     }
 }

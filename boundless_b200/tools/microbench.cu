@@ -144,6 +144,16 @@ int main() {
     int ok2 = 1; for (int i = 0; i < 24; i++) ok2 &= (h2[i] == KAT[i]) && (h2[24 + i] == KAT[i]);
     printf("poseidon2_kat2 (two interleaved states) %s\n", ok2 ? "PASS" : "FAIL");
 
+#ifdef B200_MB_QUICK      // variant sweeps: the KAT and three launch shapes of the permutation only
+    {
+        int pit = 64;
+#define PERMQ(T, MB, BPS) { int nb = sms * BPS; float ms = time_ms([&] { k_perm<T, MB><<<nb, T>>>(d_out, pit, 7u); }); \
+            double perms = (double)nb * T * pit; printf("perm threads=%d minb=%d blocks/sm=%d %.3f Gperm/s\n", T, MB, BPS, perms / ms * 1e-6); }
+        PERMQ(256, 3, 6) PERMQ(256, 2, 6) PERMQ(512, 1, 2) PERMQ(1024, 1, 1)
+    }
+    CK(cudaFree(d_out));
+    return ok ? 0 : 1;
+#endif
     const char* names[] = {"imad_lo_rrr", "imad_hi_rr", "imad_wide", "iadd", "viaddmin_u32", "imad_lo_imm", "imad_hi_imm", "lop3", "shf"};
     int blocks = sms * 8, iters = 2000;
     double ops = (double)blocks * 256 * iters * 32;
