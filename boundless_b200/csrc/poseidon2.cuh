@@ -113,25 +113,59 @@ __device__ __forceinline__ void p2_m_int(uint32_t (&c)[24]) {
     for (int i = 0; i < 24; i++) c[i] = fp_mul_acc(c_diag[i], c[i], X);
 }
 
+// loop unrolling of the round loops (instruction-cache footprint against scheduling freedom across rounds; measured with
+// tools/microbench.cu, profiles/microbench_unroll_r01.txt)
+#ifndef B200_P2_UNROLL_EXT
+#define B200_P2_UNROLL_EXT 1
+#endif
+#ifndef B200_P2_UNROLL_INT
+#define B200_P2_UNROLL_INT 1
+#endif
+#define B200_PRAGMA(x) _Pragma(#x)
+#define B200_UNROLL(n) B200_PRAGMA(unroll n)
+#ifndef B200_P2_MERGED
+#define B200_P2_MERGED 0
+#endif
 __device__ __forceinline__ void p2_permute(uint32_t (&c)[24]) {
     p2_m_ext(c);
+#if B200_P2_MERGED
+    // one copy of the full-round body serves the first and the last four rounds (smaller instruction footprint)
 #pragma unroll 1
+    for (int phase = 0; phase < 2; phase++) {
+        const int base = phase ? 117 : 0;
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int i = 0; i < 24; i++) c[i] = p2_sbox(P2_ADD_RC(c[i], c_rc[base + 24 * r + i]));
+            p2_m_ext(c);
+        }
+        if (phase == 0) {
+#pragma unroll 1
+            for (int r = 0; r < 21; r++) {
+                c[0] = p2_sbox(P2_ADD_RC(c[0], c_rc[96 + r]));
+                p2_m_int(c);
+            }
+        }
+    }
+#else
+B200_UNROLL(B200_P2_UNROLL_EXT)
     for (int r = 0; r < 4; r++) {
 #pragma unroll
         for (int i = 0; i < 24; i++) c[i] = p2_sbox(P2_ADD_RC(c[i], c_rc[24 * r + i]));
         p2_m_ext(c);
     }
-#pragma unroll 1
+B200_UNROLL(B200_P2_UNROLL_INT)
     for (int r = 0; r < 21; r++) {
         c[0] = p2_sbox(P2_ADD_RC(c[0], c_rc[96 + r]));
         p2_m_int(c);
     }
-#pragma unroll 1
+B200_UNROLL(B200_P2_UNROLL_EXT)
     for (int r = 0; r < 4; r++) {
 #pragma unroll
         for (int i = 0; i < 24; i++) c[i] = p2_sbox(P2_ADD_RC(c[i], c_rc[117 + 24 * r + i]));
         p2_m_ext(c);
     }
+#endif
 }
 
 // Two independent states per thread, software-pipelined by half a round: while state A is in its (ALU-heavy) linear

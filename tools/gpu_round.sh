@@ -18,4 +18,6 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_f
     -c 12 -f -o $O/ncu_hal_$TAG python tools/prof_kernels.py hal > $O/ncu_hal_$TAG.log 2>&1; echo "ncu hal exit $?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_p2_fold' -c 1 -f -o $O/ncu_fold_$TAG \
     python tools/prof_kernels.py fold > $O/ncu_fold_$TAG.log 2>&1; echo "ncu fold exit $?"
-ls -la $O | tail -20
+
+timeout 300 python tools/ntt_sweep.py > $O/ntt_sweep_$TAG.jsonl 2> $O/ntt_sweep_$TAG.err; echo "sweep exit $?"
+timeout 120 python tools/time_ntt2.py > $O/time_ntt2_$TAG.log 2>&1
