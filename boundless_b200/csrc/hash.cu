@@ -61,9 +61,10 @@ __global__ void __launch_bounds__(256, 2) k_p2_fold(uint32_t* __restrict__ out, 
     o[0] = make_uint4(st[0], st[1], st[2], st[3]);
     o[1] = make_uint4(st[4], st[5], st[6], st[7]);
 }
-// top of the tree: layers with <= 1024 nodes handled by one CTA
+// top of the tree: layers with <= 1024 nodes handled by one CTA.  Wide layers (>= 64 nodes) use one thread per node; the last six
+// layers (32 ... 1 nodes), where a one-thread permutation would leave the CTA waiting ~23 us per layer, use one WARP per node.
 __global__ void __launch_bounds__(1024, 1) k_p2_fold_top(uint32_t* nodes, uint32_t top_nodes) {
-    for (uint32_t sz = top_nodes; sz >= 1; sz >>= 1) {
+    for (uint32_t sz = top_nodes; sz >= 64; sz >>= 1) {
         const uint32_t j = threadIdx.x;
         if (j < sz) {
             const uint32_t i = sz + j;
@@ -73,6 +74,19 @@ __global__ void __launch_bounds__(1024, 1) k_p2_fold_top(uint32_t* nodes, uint32
             uint4* o = reinterpret_cast<uint4*>(nodes + (size_t)i * 8);
             o[0] = make_uint4(st[0], st[1], st[2], st[3]);
             o[1] = make_uint4(st[4], st[5], st[6], st[7]);
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(1024, 1) k_p2_fold_top_w(uint32_t* nodes, uint32_t top_nodes) {
+    P2Warp w; w.init();
+    const uint32_t wid = threadIdx.x >> 5;
+    for (uint32_t sz = top_nodes; sz >= 1; sz >>= 1) {
+        if (wid < sz) {
+            const uint32_t i = sz + wid;
+            uint32_t x = w.lane < 16 ? nodes[(size_t)i * 16 + w.lane] : 0u;
+            x = w.permute(x);
+            if (w.lane < 8) nodes[(size_t)i * 8 + w.lane] = x;
         }
         __syncthreads();
     }
@@ -104,83 +118,74 @@ cudaError_t launch_poseidon2_fold_tree(uint32_t* d_nodes, uint32_t lg_rows, cuda
         if (e != cudaSuccess) return e;
         sz >>= 1;
     }
-    B200_LAUNCH(k_p2_fold_top)<<<1, 1024, 0, s>>>(d_nodes, sz);
+    if (sz >= 64) B200_LAUNCH(k_p2_fold_top)<<<1, 1024, 0, s>>>(d_nodes, sz);
+    B200_LAUNCH(k_p2_fold_top_w)<<<1, 1024, 0, s>>>(d_nodes, sz < 32 ? sz : 32u);
     return cudaGetLastError();
 }
 
 // Transcript (Poseidon2Rng) -----------------------------------------------------------
-__device__ __forceinline__ void tr_load(uint32_t (&c)[24], const Transcript* t) {
-#pragma unroll
-    for (int i = 0; i < 24; i++) c[i] = t->cells[i];
+// The transcript kernels run as ONE WARP (P2Warp, poseidon2.cuh): they are single permutation chains on the proof's critical path.
+__device__ __forceinline__ uint32_t tr_load_w(const P2Warp& w, const Transcript* t) { return w.lane < 24 ? t->cells[w.lane] : 0u; }
+__device__ __forceinline__ void tr_store_w(const P2Warp& w, Transcript* t, uint32_t x, uint32_t used) {
+    if (w.lane < 24) t->cells[w.lane] = x;
+    if (w.lane == 0) t->pool_used = used;
 }
-__device__ __forceinline__ void tr_store(Transcript* t, const uint32_t (&c)[24], uint32_t used) {
-#pragma unroll
-    for (int i = 0; i < 24; i++) t->cells[i] = c[i];
-    t->pool_used = used;
-}
-__device__ __forceinline__ void sponge_elems(uint32_t (&st)[24], const uint32_t* __restrict__ e, uint32_t count) {
-#pragma unroll
-    for (int i = 0; i < 24; i++) st[i] = 0;
-    uint32_t k = 0;
+// overwrite-mode sponge over `count` elements; returns this lane's cell (digest = lanes 0..7)
+__device__ __forceinline__ uint32_t sponge_elems_w(const P2Warp& w, const uint32_t* __restrict__ e, uint32_t count) {
+    uint32_t x = 0, k = 0;
     for (; k + 16 <= count; k += 16) {
-#pragma unroll
-        for (int i = 0; i < 16; i++) st[i] = e[k + i];
-        p2_permute(st);
+        if (w.lane < 16) x = e[k + w.lane];
+        x = w.permute(x);
     }
     const uint32_t rem = count - k;
     if (rem != 0 || count == 0) {
-#pragma unroll
-        for (int i = 0; i < 16; i++) st[i] = (uint32_t)i < rem ? e[k + i] : 0u;
-        p2_permute(st);
+        if (w.lane < 16) x = w.lane < rem ? e[k + w.lane] : 0u;
+        x = w.permute(x);
     }
+    return x;
 }
 __global__ void k_iop_init(Transcript* t) {
     for (int i = 0; i < 24; i++) t->cells[i] = 0;
     t->pool_used = 0;
 }
-__global__ void k_iop_commit(Transcript* t, const uint32_t* __restrict__ digest) {
-    uint32_t c[24]; tr_load(c, t);
-#pragma unroll
-    for (int i = 0; i < 8; i++) c[i] = fp_add(c[i], digest[i]);
-    p2_permute(c);
-    tr_store(t, c, 0);
+__global__ void __launch_bounds__(32) k_iop_commit(Transcript* t, const uint32_t* __restrict__ digest) {
+    P2Warp w; w.init();
+    uint32_t x = tr_load_w(w, t);
+    if (w.lane < 8) x = fp_add(x, digest[w.lane]);
+    tr_store_w(w, t, w.permute(x), 0);
 }
-__global__ void k_iop_commit_elems(Transcript* t, const uint32_t* __restrict__ elems, uint32_t count, uint32_t* digest_out) {
-    uint32_t st[24];
-    sponge_elems(st, elems, count);
-    if (digest_out) for (int i = 0; i < 8; i++) digest_out[i] = st[i];
-    uint32_t c[24]; tr_load(c, t);
-#pragma unroll
-    for (int i = 0; i < 8; i++) c[i] = fp_add(c[i], st[i]);
-    p2_permute(c);
-    tr_store(t, c, 0);
+__global__ void __launch_bounds__(32) k_iop_commit_elems(Transcript* t, const uint32_t* __restrict__ elems, uint32_t count, uint32_t* digest_out) {
+    P2Warp w; w.init();
+    const uint32_t d = sponge_elems_w(w, elems, count);
+    if (digest_out && w.lane < 8) digest_out[w.lane] = d;
+    uint32_t x = tr_load_w(w, t);
+    if (w.lane < 8) x = fp_add(x, d);
+    tr_store_w(w, t, w.permute(x), 0);
 }
-__global__ void k_hash_elems(uint32_t* digest_out, const uint32_t* __restrict__ elems, uint32_t count) {
-    uint32_t st[24];
-    sponge_elems(st, elems, count);
-    for (int i = 0; i < 8; i++) digest_out[i] = st[i];
+__global__ void __launch_bounds__(32) k_hash_elems(uint32_t* digest_out, const uint32_t* __restrict__ elems, uint32_t count) {
+    P2Warp w; w.init();
+    const uint32_t d = sponge_elems_w(w, elems, count);
+    if (w.lane < 8) digest_out[w.lane] = d;
 }
-__global__ void k_hash_pair_one(uint32_t* out, const uint32_t* a, const uint32_t* b) {
-    uint32_t st[24];
-    for (int i = 0; i < 8; i++) { st[i] = a[i]; st[8 + i] = b[i]; st[16 + i] = 0; }
-    p2_permute(st);
-    for (int i = 0; i < 8; i++) out[i] = st[i];
+__global__ void __launch_bounds__(32) k_hash_pair_one(uint32_t* out, const uint32_t* a, const uint32_t* b) {
+    P2Warp w; w.init();
+    uint32_t x = w.lane < 8 ? a[w.lane] : (w.lane < 16 ? b[w.lane - 8] : 0u);
+    x = w.permute(x);
+    if (w.lane < 8) out[w.lane] = x;
 }
 // draws n elems; bits == 0 -> raw Montgomery elems, else as_u32() & mask
-__global__ void k_iop_draw(Transcript* t, uint32_t* out, uint32_t n, uint32_t bits) {
-    uint32_t c[24]; tr_load(c, t);
+__global__ void __launch_bounds__(32) k_iop_draw(Transcript* t, uint32_t* out, uint32_t n, uint32_t bits) {
+    P2Warp w; w.init();
+    uint32_t x = tr_load_w(w, t);
     uint32_t used = t->pool_used;
     for (uint32_t k = 0; k < n; k++) {
-        if (used == 16) { p2_permute(c); used = 0; }
-        uint32_t v = 0;
-        // register array indexed dynamically: select
-#pragma unroll
-        for (int i = 0; i < 16; i++) if ((uint32_t)i == used) v = c[i];
+        if (used == 16) { x = w.permute(x); used = 0; }
+        uint32_t v = __shfl_sync(0xffffffffu, x, used);
         used++;
         if (bits) { v = fp_from_mont(v); if (bits < 32) v &= (1u << bits) - 1; }
-        out[k] = v;
+        if (w.lane == 0) out[k] = v;
     }
-    tr_store(t, c, used);
+    tr_store_w(w, t, x, used);
 }
 
 // seal[0..8) = circuit header; seal[8..16) = digest of the segment seed (segments) or left for the caller (recursion)
@@ -203,21 +208,21 @@ cudaError_t launch_set_globals(uint32_t* d_seal, uint32_t po2, uint32_t w_code, 
 }
 
 cudaError_t launch_iop_init(Transcript* t, cudaStream_t s) { B200_LAUNCH(k_iop_init)<<<1, 1, 0, s>>>(t); return cudaGetLastError(); }
-cudaError_t launch_iop_commit(Transcript* t, const uint32_t* d, cudaStream_t s) { B200_LAUNCH(k_iop_commit)<<<1, 1, 0, s>>>(t, d); return cudaGetLastError(); }
+cudaError_t launch_iop_commit(Transcript* t, const uint32_t* d, cudaStream_t s) { B200_LAUNCH(k_iop_commit)<<<1, 32, 0, s>>>(t, d); return cudaGetLastError(); }
 cudaError_t launch_iop_commit_elems(Transcript* t, const uint32_t* e, uint32_t count, uint32_t* dout, cudaStream_t s) {
-    B200_LAUNCH(k_iop_commit_elems)<<<1, 1, 0, s>>>(t, e, count, dout); return cudaGetLastError();
+    B200_LAUNCH(k_iop_commit_elems)<<<1, 32, 0, s>>>(t, e, count, dout); return cudaGetLastError();
 }
 cudaError_t launch_iop_draw_ext(Transcript* t, uint32_t* out, uint32_t n_ext, cudaStream_t s) {
-    B200_LAUNCH(k_iop_draw)<<<1, 1, 0, s>>>(t, out, n_ext * 4, 0); return cudaGetLastError();
+    B200_LAUNCH(k_iop_draw)<<<1, 32, 0, s>>>(t, out, n_ext * 4, 0); return cudaGetLastError();
 }
 cudaError_t launch_iop_draw_bits(Transcript* t, uint32_t* out, uint32_t n, uint32_t bits, cudaStream_t s) {
-    B200_LAUNCH(k_iop_draw)<<<1, 1, 0, s>>>(t, out, n, bits); return cudaGetLastError();
+    B200_LAUNCH(k_iop_draw)<<<1, 32, 0, s>>>(t, out, n, bits); return cudaGetLastError();
 }
 cudaError_t launch_hash_elems(uint32_t* dout, const uint32_t* e, uint32_t count, cudaStream_t s) {
-    B200_LAUNCH(k_hash_elems)<<<1, 1, 0, s>>>(dout, e, count); return cudaGetLastError();
+    B200_LAUNCH(k_hash_elems)<<<1, 32, 0, s>>>(dout, e, count); return cudaGetLastError();
 }
 cudaError_t launch_hash_pair_one(uint32_t* out, const uint32_t* a, const uint32_t* b, cudaStream_t s) {
-    B200_LAUNCH(k_hash_pair_one)<<<1, 1, 0, s>>>(out, a, b); return cudaGetLastError();
+    B200_LAUNCH(k_hash_pair_one)<<<1, 32, 0, s>>>(out, a, b); return cudaGetLastError();
 }
 
 }  // namespace b200

@@ -168,6 +168,61 @@ B200_UNROLL(B200_P2_UNROLL_EXT)
 #endif
 }
 
+// ---- warp-cooperative permutation (latency form) ----------------------------------------------------------------
+// One WARP per state: lane i < 24 holds cell i, lanes 24..31 hold 0 and take part in the shuffles.  Used where a single
+// permutation chain is on a proof's critical path (Fiat-Shamir transcript, hash of the tap evaluations, the top of a Merkle
+// tree): 24 S-boxes / 24 diagonal multiplies run in parallel and the linear layers are shuffles, so one permutation takes
+// ~4 us instead of ~23 us for the one-thread form.  Same field operations on canonical values => bit-identical results.
+static __device__ const uint32_t g_rc_w[213] = B200_P2_RC_INIT;      // lane-indexed reads: global memory, not the constant bank
+static __device__ const uint32_t g_diag_w[24] = B200_P2_DIAG_INIT;
+
+struct P2Warp {
+    uint32_t lane, m4[4], diag;       // this lane's M4 row (Montgomery form of the small integers) and diagonal entry
+    uint32_t rc[8];                   // this lane's round constant of each full round
+    __device__ __forceinline__ void init() {
+        lane = threadIdx.x & 31u;
+        const uint32_t r = lane & 3u;
+        // M4 = [[5,7,1,3],[4,6,1,1],[1,3,5,7],[1,1,4,6]]
+        const uint32_t row = r == 0 ? 0x03010705u : r == 1 ? 0x01010604u : r == 2 ? 0x07050301u : 0x06040101u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) m4[j] = fp_to_mont((row >> (8 * j)) & 0xffu);
+        diag = lane < 24 ? g_diag_w[lane] : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) rc[k] = lane < 24 ? g_rc_w[(k < 4 ? 24 * k : 117 + 24 * (k - 4)) + lane] : 0u;
+    }
+    __device__ __forceinline__ uint32_t m_ext(uint32_t x) const {
+        const uint32_t q = lane & ~3u;
+        const uint32_t x0 = __shfl_sync(0xffffffffu, x, q), x1 = __shfl_sync(0xffffffffu, x, q + 1);
+        const uint32_t x2 = __shfl_sync(0xffffffffu, x, q + 2), x3 = __shfl_sync(0xffffffffu, x, q + 3);
+        const uint32_t y = fp_add(fp_add(fp_mul(m4[0], x0), fp_mul(m4[1], x1)), fp_add(fp_mul(m4[2], x2), fp_mul(m4[3], x3)));
+        uint32_t s = y;                                   // column sums over the 8 quads (quads 6, 7 are zero)
+        s = fp_add(s, __shfl_xor_sync(0xffffffffu, s, 4));
+        s = fp_add(s, __shfl_xor_sync(0xffffffffu, s, 8));
+        s = fp_add(s, __shfl_xor_sync(0xffffffffu, s, 16));
+        return lane < 24 ? fp_add(y, s) : 0u;
+    }
+    __device__ __forceinline__ uint32_t permute(uint32_t x) const {
+        x = m_ext(x);
+#pragma unroll
+        for (int r = 0; r < 4; r++) x = m_ext(p2_sbox(fp_add(x, rc[r])));      // lanes >= 24: sbox(0) = 0
+#pragma unroll 1
+        for (int r = 0; r < 21; r++) {
+            // sum of cells 1..23 by butterfly shuffles, concurrently with the S-box of cell 0
+            uint32_t s = lane == 0 ? 0u : x;
+            const uint32_t x0 = p2_sbox(fp_add(x, c_rc[96 + r]));                 // only lane 0's value is used
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) s = fp_add(s, __shfl_xor_sync(0xffffffffu, s, d));
+            const uint32_t c0 = __shfl_sync(0xffffffffu, x0, 0);
+            s = fp_add(s, c0);
+            if (lane == 0) x = c0;
+            x = lane < 24 ? fp_add(fp_mul(diag, x), s) : 0u;
+        }
+#pragma unroll
+        for (int r = 4; r < 8; r++) x = m_ext(p2_sbox(fp_add(x, rc[r])));
+        return x;
+    }
+};
+
 // Two independent states per thread, software-pipelined by half a round: while state A is in its (ALU-heavy) linear
 // layer, state B is in its (multiplier-heavy) S-box layer, so both integer pipes stay busy inside one warp.
 __device__ __forceinline__ void p2_sbox_full(uint32_t (&c)[24], int rc_base) {
