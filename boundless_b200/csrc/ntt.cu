@@ -935,7 +935,13 @@ static uint32_t strided_lgTW(uint32_t logL) {
     if (lg < 3) lg = 3;
     return lg;
 }
-static uint32_t split_n1(uint32_t lg) { uint32_t n1 = lg / 2; return n1 > 11 ? 11 : n1; }
+// N = N1 * N2 with the strided pass over N1 rows.  2^10 rows is the shape the radix-32 register kernel covers, so it is preferred
+// whenever the contiguous pass then has rows of 2^8 .. 2^13 (sizes 2^18 .. 2^23); otherwise the balanced split.
+static uint32_t split_n1(uint32_t lg, uint32_t lg_e = 0) {
+    if (lg >= 18 && lg + lg_e <= 23 && env_int("B200_NTT_SPLIT10", 1)) return 10;
+    uint32_t n1 = lg / 2;
+    return n1 > 11 ? 11 : n1;
+}
 
 template <bool DIF>
 static cudaError_t run_strided(const DeviceTables* T, uint32_t* d, uint32_t logL, uint32_t row_stride, uint32_t ncols, uint32_t count,
@@ -1088,7 +1094,7 @@ cudaError_t launch_batch_expand_ntt(const DeviceTables* T, uint32_t* d_out, cons
     const size_t N = (size_t)1 << lg_n, M = (size_t)1 << lg_m;
     if (lg_m <= 13) return run_contig<false>(T, d_out, d_in, lg_m, lg_e, 1, count, N, M, nullptr, 0, 0, 0, s);
     if (lg_m > MAX_LG) return cudaErrorInvalidValue;
-    const uint32_t n1 = split_n1(lg_n), n2 = lg_n - n1;
+    const uint32_t n1 = split_n1(lg_n, lg_e), n2 = lg_n - n1;
     // pass 1: row rho (N2 coefficients) -> 2^lg_e * N2 values, times w_M^(i0 * bitrev(rho))
     cudaError_t e = run_contig<false>(T, d_out, d_in, n2 + lg_e, lg_e, 1u << n1, count, N, M, T->pow_fwd[lg_m], lg_m, n1, 0, s);
     if (e != cudaSuccess) return e;
