@@ -73,6 +73,7 @@ extern "C" {
     pub fn b200_prover_device_bytes(p: *const b200_prover) -> usize;
     pub fn b200_prove_segment_async(p: *mut b200_prover, slot: u32, c: *const b200_circuit, seed: u64, h_trace: *const u32,
                                     h_seal: *mut u32) -> *const c_char;
+    pub fn b200_prefetch_trace_async(p: *mut b200_prover, slot: u32, c: *const b200_circuit, h_trace: *const u32) -> *const c_char;
     pub fn b200_recursion_async(p: *mut b200_prover, slot: u32, c: *const b200_circuit, h_seal_a: *const u32, words_a: usize,
                                 h_seal_b: *const u32, words_b: usize, h_seal: *mut u32) -> *const c_char;
     pub fn b200_verify_async(p: *mut b200_prover, slot: u32, h_seal: *const u32, words: usize, h_result: *mut c_int) -> *const c_char;

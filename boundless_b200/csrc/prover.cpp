@@ -94,6 +94,11 @@ struct Slot {
     uint32_t* h_seal_out = nullptr; size_t seal_words = 0;
     uint32_t* h_stage = nullptr; size_t h_stage_words = 0;   // pinned staging for child seals
     bool busy = false;
+    // witness prefetch (b200_prefetch_trace_async): a second coefficient region filled by a copy stream while the slot proves
+    uint32_t* coeffs_alt = nullptr; size_t coeffs_words = 0;
+    uint32_t* alt_alloc = nullptr;            // the cudaMalloc'ed region (coeffs / coeffs_alt swap roles, this is what gets freed)
+    cudaStream_t copy_stream = nullptr; cudaEvent_t ev_staged = nullptr;
+    const uint32_t* staged_src = nullptr; size_t staged_words = 0;
     b200_circuit last_circuit{}; bool has_seal = false;     // what s.seal holds (for verify of the slot's own proof)
 };
 
@@ -137,7 +142,7 @@ static const char* slot_init(b200_prover* p, Slot& s) {
     CU(cudaMalloc(&s.arena.base, s.arena.words * 4));
     p->device_bytes += s.arena.words * 4;
     Arena& a = s.arena;
-    s.coeffs = a.take(W * N); s.evals = a.take(W * D); s.check_coeffs = a.take(CHECK_COLS * N); s.check_evals = a.take(CHECK_COLS * D);
+    s.coeffs = a.take(W * N); s.coeffs_words = W * N; s.evals = a.take(W * D); s.check_coeffs = a.take(CHECK_COLS * N); s.check_evals = a.take(CHECK_COLS * D);
     for (int g = 0; g < 4; g++) s.nodes[g] = a.take(2 * D * 8);
     s.fri_evals = a.take(16 * N + 16 * N / 8); s.fri_nodes = a.take(8 * N + 4096); s.fri_coeffs = a.take(4 * N);
     s.combos = a.take(12 * N); s.f_planes = a.take(4 * N);
@@ -175,7 +180,7 @@ static const char* commit_group(b200_prover* p, Slot& s, uint32_t* coeffs, uint3
 // The proof proper.  Precondition: s.seal[8..16) (input digest) is already being produced on s.stream, and for
 // recursion kinds s.digests[0..2) holds the trace seed words.
 static const char* prove_on_slot(b200_prover* p, Slot& s, const b200_circuit& c, uint64_t seed, bool seed_on_device,
-                                 const uint32_t* h_trace, uint32_t* h_seal) {
+                                 const uint32_t* h_trace, uint32_t* h_seal, bool witness_staged = false) {
     cudaStream_t st = s.stream;
     const uint32_t po2 = c.po2, N = 1u << po2, D = 4 * N;
     const uint32_t W = c.w_code + c.w_data + c.w_accum, T = W + c.w_accum + CHECK_COLS;
@@ -188,7 +193,8 @@ static const char* prove_on_slot(b200_prover* p, Slot& s, const b200_circuit& c,
 
     // witness: host trace (H2D) or the witgen stand-in
     const size_t tw = (size_t)(c.w_code + c.w_data) * N;
-    if (h_trace) CU(cudaMemcpyAsync(code, h_trace, tw * 4, cudaMemcpyHostToDevice, st));
+    if (witness_staged) { /* already in `code` (prefetched; the stream waits on ev_staged) */ }
+    else if (h_trace) CU(cudaMemcpyAsync(code, h_trace, tw * 4, cudaMemcpyHostToDevice, st));
     else KL(launch_gen_trace(code, seed, seed_on_device ? s.digests : nullptr, tw, st));
     CU(cudaMemcpyAsync(accum, data, (size_t)c.w_accum * N * 4, cudaMemcpyDeviceToDevice, st));   // raw data columns for accumulate
 
@@ -385,6 +391,9 @@ void b200_prover_destroy(b200_prover* p) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         if (s.arena.base) cudaFree(s.arena.base);
         if (s.h_stage) cudaFreeHost(s.h_stage);
+        if (s.alt_alloc) cudaFree(s.alt_alloc);
+        if (s.ev_staged) cudaEventDestroy(s.ev_staged);
+        if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
         if (s.ev_begin) cudaEventDestroy(s.ev_begin);
         if (s.ev_end) cudaEventDestroy(s.ev_end);
         for (int i = 0; i < 2; i++) if (s.ev_mark[i]) cudaEventDestroy(s.ev_mark[i]);
@@ -415,7 +424,43 @@ const char* b200_prove_segment_async(b200_prover* p, uint32_t slot, const b200_c
     Slot& s = p->slots[slot];
     CU(cudaEventRecord(s.ev_begin, s.stream));
     KL(launch_set_globals(s.seal, c->po2, c->w_code, c->w_data, c->w_accum, c->kind, seed, 1, s.stream));
-    return prove_on_slot(p, s, *c, seed, false, h_trace, h_seal);
+    bool staged = false;
+    if (h_trace && s.staged_src == h_trace && s.staged_words == ((size_t)(c->w_code + c->w_data) << c->po2)) {
+        // the witness was prefetched into the other coefficient region: make that region the current one
+        CU(cudaStreamWaitEvent(s.stream, s.ev_staged, 0));
+        uint32_t* t = s.coeffs; s.coeffs = s.coeffs_alt; s.coeffs_alt = t;
+        staged = true;
+    }
+    s.staged_src = nullptr; s.staged_words = 0;
+    return prove_on_slot(p, s, *c, seed, false, h_trace, h_seal, staged);
+}
+
+// Copy the NEXT segment's witness host -> device on the slot's copy stream while the slot is still proving the current one; the
+// following b200_prove_segment_async with the same h_trace pointer picks it up without a copy on its own stream.
+const char* b200_prefetch_trace_async(b200_prover* p, uint32_t slot, const b200_circuit* c, const uint32_t* h_trace) {
+    if (!p) { set_error("b200: null prover"); return last_error(); }
+    if (slot >= p->slots.size()) { set_error("b200: slot %u out of range", slot); return last_error(); }
+    const char* ce = check_circuit(c);
+    if (ce) { set_error("%s", ce); return last_error(); }
+    if (!h_trace) { set_error("b200: null h_trace"); return last_error(); }
+    Slot& s = p->slots[slot];
+    const size_t tw = (size_t)(c->w_code + c->w_data) << c->po2;
+    if (c->po2 > p->maxc.po2 || ((size_t)(c->w_code + c->w_data + c->w_accum) << c->po2) > s.coeffs_words) {
+        set_error("b200: circuit exceeds the prover's max_circuit"); return last_error();
+    }
+    CU(cudaSetDevice(p->device));
+    if (!s.coeffs_alt) {      // first use on this slot: a synchronising allocation, keep it out of timed regions (warm up with one prefetch)
+        CU(cudaMalloc(&s.alt_alloc, s.coeffs_words * 4));
+        s.coeffs_alt = s.alt_alloc;
+        p->device_bytes += s.coeffs_words * 4;
+        CU(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s.ev_staged, cudaEventDisableTiming));
+    }
+    // coeffs_alt was the region of this slot's previous proof, which the caller has already waited for
+    CU(cudaMemcpyAsync(s.coeffs_alt, h_trace, tw * 4, cudaMemcpyHostToDevice, s.copy_stream));
+    CU(cudaEventRecord(s.ev_staged, s.copy_stream));
+    s.staged_src = h_trace; s.staged_words = tw;
+    return nullptr;
 }
 
 const char* b200_recursion_async(b200_prover* p, uint32_t slot, const b200_circuit* c, const uint32_t* h_a, size_t wa,

@@ -65,6 +65,7 @@ SYMBOLS = {
     "b200_prover_destroy": (None, [_vp]),
     "b200_prover_device_bytes": (_sz, [_vp]),
     "b200_prove_segment_async": (_cp, [_vp, _u32, C.POINTER(Circuit), _u64, _vp, _vp]),
+    "b200_prefetch_trace_async": (_cp, [_vp, _u32, C.POINTER(Circuit), _vp]),
     "b200_recursion_async": (_cp, [_vp, _u32, C.POINTER(Circuit), _vp, _sz, _vp, _sz, _vp]),
     "b200_verify_async": (_cp, [_vp, _u32, _vp, _sz, C.POINTER(C.c_int)]),
     "b200_prover_wait": (_cp, [_vp, _u32]),

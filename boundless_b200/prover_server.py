@@ -117,6 +117,7 @@ class ProverServer:
         max_words = max(self.seal_words(self.seg_circuit), self.seal_words(self._rec_circuit(KIND_LIFT)))
         self._seal_bufs = [_Pinned(self.L, max_words) for _ in range(opts.slots)]
         self._pending = [None] * opts.slots
+        self._prefetched = [None] * opts.slots
         self._verdict = [C.c_int(0) for _ in range(opts.slots)]
 
     # -- helpers -------------------------------------------------------------------------------------------
@@ -163,6 +164,19 @@ class ProverServer:
                                                     tr.ctypes.data_as(C.c_void_p) if tr is not None else None,
                                                     self._buf(slot)))
         self._pending[slot] = ("segment", c, segment, tr)
+
+    def prefetch_segment(self, slot, segment: Segment):
+        """Start the host -> device copy of `segment.trace` for the NEXT proof of `slot` while the slot is still proving; the
+        following submit_segment(slot, segment) with the same trace buffer then starts without a copy on its own stream."""
+        if segment.trace is None:
+            return
+        c = Circuit(segment.po2, *self.opts.segment_widths, KIND_SEGMENT)
+        tr = np.ascontiguousarray(segment.trace, dtype=np.uint32)
+        need = (c.w_code + c.w_data) << c.po2
+        if tr.size != need:
+            raise B200Error("segment trace has %d words, expected %d" % (tr.size, need))
+        _lib.check(self.L.b200_prefetch_trace_async(self.h, slot, C.byref(c), tr.ctypes.data_as(C.c_void_p)))
+        self._prefetched[slot] = tr          # keep the buffer alive until it is consumed
 
     def submit_recursion(self, slot, kind, a, b=None):
         c = self._rec_circuit(kind)

@@ -97,6 +97,7 @@ class Agent:
         self.args = args or AgentArgs()
         self.povw = povw
         self.processed: List[str] = []          # "<job>|<task>" in completion order (for tests / tracing)
+        self.errors: List[str] = []             # "<job>|<task>: <error>" of every failed attempt, retried or not
 
     # hot store helpers (lib.rs hot_get_bytes / hot_set_bytes / hot_delete)
     def hot_get_bytes(self, key): return self.store.get_bytes(key)
@@ -367,6 +368,7 @@ def poll_work(agent: Agent, max_tasks: Optional[int] = None) -> int:
             continue
         except Exception as err:          # noqa: BLE001
             err_str = str(err)
+            agent.errors.append("%s|%s: %s" % (task.job_id, task.task_id, err_str))
         if task.max_retries > 0:
             current = db.get_task_retries_running(task.job_id, task.task_id)
             if current is not None and current + 1 > task.max_retries:

@@ -124,6 +124,11 @@ size_t b200_prover_device_bytes(const b200_prover* p);
  * h_seal receives b200_seal_words(c) words once b200_prover_wait(p, slot) returns. */
 const char* b200_prove_segment_async(b200_prover* p, uint32_t slot, const b200_circuit* c, uint64_t seed,
                                      const uint32_t* h_trace, uint32_t* h_seal);
+/* Overlap the host -> device copy of the NEXT segment's witness with the proof the slot is running: copies h_trace (pinned) into the
+ * slot's second coefficient region on a separate copy stream; the next b200_prove_segment_async on this slot that passes the SAME
+ * h_trace pointer uses it without copying on its own stream.  May be called while the slot is busy; the caller must have waited for
+ * the slot's previous proof but one (true for any submit / wait loop).  The region (W x 2^po2 words) is allocated on first use. */
+const char* b200_prefetch_trace_async(b200_prover* p, uint32_t slot, const b200_circuit* c, const uint32_t* h_trace);
 /* lift / join / resolve / union: recursion-shaped proof (kind 1..4) over the digest(s) of the child seal(s) */
 const char* b200_recursion_async(b200_prover* p, uint32_t slot, const b200_circuit* c, const uint32_t* h_seal_a,
                                  size_t words_a, const uint32_t* h_seal_b, size_t words_b, uint32_t* h_seal);

@@ -46,6 +46,33 @@ def test_segment_from_host_trace(small_server, oracle):
     assert oracle.verify(rcpt2.seal) == 0
 
 
+def test_prefetched_witness_gives_the_same_seal(small_server, oracle):
+    """b200_prefetch_trace_async: the next witness is copied on the copy stream into the slot's second coefficient region while the
+    slot is proving; seals are bit-identical to the plain path, the regions alternate, and an unrelated trace is not confused."""
+    from boundless_b200 import Segment
+    po2, srv = 12, small_server
+    seeds = [0xB2000000 + 900 + i for i in range(4)]
+    traces = [oracle.gen_trace(sd, po2, 16 + 208) for sd in seeds]
+    segs = [Segment(index=900 + i, po2=po2, seed=sd, trace=t) for i, (sd, t) in enumerate(zip(seeds, traces))]
+    refs = [oracle.prove(po2, sd) for sd in seeds]
+    seals = []
+    srv.submit_segment(0, segs[0])
+    for i in range(1, 4):
+        srv.prefetch_segment(0, segs[i])             # under the running proof
+        seals.append(srv.wait(0).seal)
+        srv.submit_segment(0, segs[i])               # same buffer -> picks the staged copy up
+    seals.append(srv.wait(0).seal)
+    for got, ref in zip(seals, refs):
+        assert np.array_equal(got, ref)
+    # a prefetch that is NOT followed by the matching submit is simply dropped
+    srv.prefetch_segment(0, segs[1])
+    other = Segment(index=950, po2=po2, seed=seeds[2], trace=traces[2].copy())
+    srv.submit_segment(0, other)
+    assert np.array_equal(srv.wait(0).seal, refs[2])
+    srv.submit_segment(0, segs[3])
+    assert np.array_equal(srv.wait(0).seal, refs[3])
+
+
 def test_lift_join_bit_exact(small_server, oracle):
     from boundless_b200 import Segment, VerifierContext
     from boundless_b200.prover_server import KIND_JOIN, KIND_LIFT, RECURSION_WIDTHS

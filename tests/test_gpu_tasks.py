@@ -27,7 +27,8 @@ def test_job_through_the_agent_loop(gpu, oracle):
         launches0 = gpu.cuda.is_available() and srv.L.b200_kernel_launches()
         assert tasks.poll_work(tasks.Agent(db, store, None, tasks.AgentArgs(task_stream=wire.EXEC_WORK_TYPE))) == 1
         gpu_agent = tasks.Agent(db, store, srv, tasks.AgentArgs(task_stream=wire.PROVE_WORK_TYPE))
-        assert tasks.poll_work(gpu_agent) == n + (n - 1) + 1
+        claimed = tasks.poll_work(gpu_agent)
+        assert gpu_agent.errors == [] and claimed == n + (n - 1) + 1
         assert tasks.poll_work(tasks.Agent(db, store, srv, tasks.AgentArgs(task_stream=wire.AUX_WORK_TYPE))) == 1
         assert db.job_state(job) == "done", db.job_error(job)
         assert srv.L.b200_kernel_launches() > launches0
