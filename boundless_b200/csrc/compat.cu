@@ -54,6 +54,15 @@ static std::mutex g_div_mu;
 static uint32_t* g_div_scratch = nullptr;
 static size_t g_div_words = 0;
 
+namespace b200 {
+// b200_shutdown(): release the division arena
+void compat_release() {
+    std::lock_guard<std::mutex> lock(g_div_mu);
+    if (g_div_scratch) cudaFree(g_div_scratch);
+    g_div_scratch = nullptr; g_div_words = 0;
+}
+}  // namespace b200
+
 extern "C" {
 
 sppark_error sppark_init(void) {

@@ -184,6 +184,7 @@ static bool have_device() { int n = 0; return cudaGetDeviceCount(&n) == cudaSucc
 extern "C" {
 
 const char* b200_shutdown(void) {
+    compat_release();
     free_tables();
     return nullptr;
 }

@@ -39,6 +39,7 @@ struct DeviceTables {
 };
 const DeviceTables* get_tables(int device);   // lazily built, thread-safe; nullptr + error string on failure
 void free_tables();                           // b200_shutdown
+void compat_release();                        // b200_shutdown: scratch arena of the risc0-sys compatible supra_poly_divide (compat.cu)
 const char* last_error();
 void set_error(const char* fmt, ...);
 
