@@ -73,6 +73,22 @@ def test_prefetched_witness_gives_the_same_seal(small_server, oracle):
     assert np.array_equal(srv.wait(0).seal, refs[3])
 
 
+def test_prove_stream_matches_the_oracle(small_server, oracle):
+    """feed.prove_stream: segments arrive from a generator with host witnesses, two proofs in flight, next witness prefetched."""
+    from boundless_b200 import Segment
+    from boundless_b200.feed import prove_stream
+    po2, n = 10, 5
+    seeds = [0xB2000000 + 700 + i for i in range(n)]
+
+    def producer():
+        for i, sd in enumerate(seeds):
+            yield Segment(index=700 + i, po2=po2, seed=sd, trace=oracle.gen_trace(sd, po2, 16 + 208))
+    receipts = list(prove_stream(small_server, producer()))
+    assert [r.index for r in receipts] == [700 + i for i in range(n)]
+    for r, sd in zip(receipts, seeds):
+        assert np.array_equal(r.seal, oracle.prove(po2, sd))
+
+
 def test_lift_join_bit_exact(small_server, oracle):
     from boundless_b200 import Segment, VerifierContext
     from boundless_b200.prover_server import KIND_JOIN, KIND_LIFT, RECURSION_WIDTHS
