@@ -12,7 +12,9 @@
 // add-min (VIADDMNMX, ALU pipe), which ptxas cannot turn into an IMAD.
 #pragma once
 #include <stdint.h>
+#ifndef B200_HOST_EMULATION      // tests/host_emul supplies the qualifiers and vector types itself
 #include <cuda_runtime.h>
+#endif
 
 namespace b200 {
 
@@ -52,7 +54,11 @@ __device__ __forceinline__ uint32_t fp_sub(uint32_t a, uint32_t b) {
 // A runtime zero the compiler cannot see through (%ctaid.z of a 1-deep grid; a uniform register, read once per thread): adding it
 // makes a sum a THREE-input add, which only IADD3 (ALU pipe) can encode -- ptxas cannot turn it into IMAD.IADD (multiplier pipe).
 // Used to steer chosen adds off the multiplier pipe in the multiplier-bound kernels (B200_P2_Z in poseidon2.cuh).
+#ifdef B200_HOST_EMULATION        // tests/host_emul compiles this header for the host: the runtime zero is a plain zero there
+__device__ __forceinline__ uint32_t zreg() { return 0u; }
+#else
 __device__ __forceinline__ uint32_t zreg() { uint32_t z; asm("mov.u32 %0, %%ctaid.z;" : "=r"(z)); return z; }
+#endif
 __device__ __forceinline__ uint32_t fp_add_z(uint32_t a, uint32_t b) {
     uint32_t s = a + b + zreg();
     return addmin(s, 0u - P, s);

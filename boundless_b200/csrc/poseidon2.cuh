@@ -173,6 +173,7 @@ B200_UNROLL(B200_P2_UNROLL_EXT)
 // permutation chain is on a proof's critical path (Fiat-Shamir transcript, hash of the tap evaluations, the top of a Merkle
 // tree): 24 S-boxes / 24 diagonal multiplies run in parallel and the linear layers are shuffles, so one permutation takes
 // ~4 us instead of ~23 us for the one-thread form.  Same field operations on canonical values => bit-identical results.
+#ifndef B200_HOST_EMULATION      // warp shuffles have no host form; tests/host_emul covers the one-thread permutation
 static __device__ const uint32_t g_rc_w[213] = B200_P2_RC_INIT;      // lane-indexed reads: global memory, not the constant bank
 static __device__ const uint32_t g_diag_w[24] = B200_P2_DIAG_INIT;
 
@@ -222,6 +223,8 @@ struct P2Warp {
         return x;
     }
 };
+
+#endif  // B200_HOST_EMULATION
 
 // Two independent states per thread, software-pipelined by half a round: while state A is in its (ALU-heavy) linear
 // layer, state B is in its (multiplier-heavy) S-box layer, so both integer pipes stay busy inside one warp.
