@@ -45,7 +45,7 @@ def edge_input(kind, n, oracle):
 
 
 @pytest.mark.parametrize("lg_n,count", [(1, 3), (4, 5), (10, 1), (10, 16), (11, 3), (12, 7), (13, 3), (14, 16), (15, 2),
-                                        (16, 16), (18, 3), (19, 2), (20, 2), (21, 2)])
+                                        (12, 272), (16, 16), (18, 3), (19, 2), (20, 2), (21, 2)])
 def test_batch_intt_and_shift(gpu, b200lib, oracle, lg_n, count):
     torch = gpu
     rng = np.random.default_rng(lg_n * 100 + count)
@@ -66,7 +66,7 @@ def test_batch_intt_and_shift(gpu, b200lib, oracle, lg_n, count):
     assert np.array_equal(host(d2), shifted)
 
 
-@pytest.mark.parametrize("lg_n,count", [(1, 2), (5, 3), (10, 4), (12, 5), (13, 2), (14, 3), (16, 4), (17, 2), (19, 2), (20, 2), (21, 1), (22, 1), (23, 1)])
+@pytest.mark.parametrize("lg_n,count", [(1, 2), (5, 3), (10, 4), (12, 5), (13, 2), (14, 3), (16, 4), (17, 2), (19, 2), (20, 2), (21, 1), (22, 1), (23, 1), (24, 1)])
 def test_batch_ntt_roundtrip(gpu, b200lib, oracle, lg_n, count):
     torch = gpu
     rng = np.random.default_rng(7 + lg_n)
@@ -86,7 +86,7 @@ def test_batch_ntt_roundtrip(gpu, b200lib, oracle, lg_n, count):
     assert np.array_equal(host(d), ref)
 
 
-@pytest.mark.parametrize("lg_n,count", [(3, 2), (8, 3), (10, 16), (11, 4), (12, 5), (13, 3), (14, 4), (16, 8), (18, 4), (19, 2), (20, 3), (21, 2)])
+@pytest.mark.parametrize("lg_n,count", [(3, 2), (8, 3), (10, 16), (11, 4), (12, 5), (13, 3), (14, 4), (12, 272), (16, 8), (18, 4), (19, 2), (20, 3), (21, 2)])
 def test_batch_expand_ntt(gpu, b200lib, oracle, lg_n, count):
     torch = gpu
     rng = np.random.default_rng(31 + lg_n)
