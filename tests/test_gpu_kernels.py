@@ -99,7 +99,7 @@ def test_batch_expand_ntt(gpu, b200lib, oracle, lg_n, count):
 
 
 @pytest.mark.parametrize("kind", EDGE)
-@pytest.mark.parametrize("lg_n", [10, 14])
+@pytest.mark.parametrize("lg_n", [10, 14, 20])
 def test_ntt_edge_inputs(gpu, b200lib, oracle, kind, lg_n):
     torch = gpu
     count = 3
