@@ -103,6 +103,14 @@ __device__ __forceinline__ uint32_t fp_mul_acc(uint32_t a, uint32_t b, uint64_t 
     uint64_t o = (uint64_t)a * b + acc64;
     return fp_redc((uint32_t)(o >> 32), (uint32_t)o);
 }
+// a*b/2^32 mod p WITHOUT the final correction: the result is in (0, 2p).  Same precondition as fp_mul (a*b < p*2^32).  A lazy value
+// may feed ONE side of a following fp_mul / Shoup multiply (those take any u32 on one side), never an add.
+__device__ __forceinline__ uint32_t fp_mul_lazy(uint32_t a, uint32_t b) {
+    uint64_t o = (uint64_t)a * b;
+    uint32_t m = (uint32_t)o * PINV;
+    uint32_t t = __umulhi(m, P);
+    return (uint32_t)(o >> 32) - t + P;      // (-p, p) + p, one three-input add
+}
 __device__ __forceinline__ uint32_t fp_sqr(uint32_t a) { return fp_mul(a, a); }
 __device__ __forceinline__ uint32_t fp_to_mont(uint32_t x) { return fp_mul(x, R2); }      // x < p
 __device__ __forceinline__ uint32_t fp_from_mont(uint32_t a) { return fp_mul(a, 1u); }

@@ -48,11 +48,39 @@ __device__ __forceinline__ uint32_t fp_add_alu(uint32_t a, uint32_t b) {
 #define P2_ADD_RC(a, b)  ((B200_P2_Z & 16) ? fp_add_z(a, b) : fp_add(a, b))
 #define P2_ADD_IS(a, b)  ((B200_P2_Z & 32) ? fp_add_z(a, b) : fp_add(a, b))
 
+// B200_P2_LAZY: instruction-count variants prepared for measurement (arithmetic checked on the host by
+// tests/test_device_code_on_host.py).  Bitmask:
+//   1  S-box: x^4 is left uncorrected in (0, 2p) -- it only feeds one side of the last multiply          (-1 instruction per S-box)
+//   2  internal layer: the 24-term sum is taken in 64 bits and reduced once                              (~ -10 per round)
+//   4  internal rounds: cells 1..23 stay lazy in [0, 2p) between rounds, the sum is carried along        (~ -7 per round)
+#ifndef B200_P2_LAZY
+#define B200_P2_LAZY 0
+#endif
 __device__ __forceinline__ uint32_t p2_sbox(uint32_t x) {
     uint32_t x2 = fp_mul(x, x);
     uint32_t x3 = fp_mul(x2, x);
+#if B200_P2_LAZY & 1
+    uint32_t x4 = fp_mul_lazy(x2, x2);
+#else
     uint32_t x4 = fp_mul(x2, x2);
+#endif
     return fp_mul(x3, x4);
+}
+// sum of `n` canonical values taken in 64 bits (no per-term correction), reduced once: acc = hi*2^32 + lo == hi*R1 + lo (mod p),
+// hi <= n*p/2^32 < 12 for n <= 24, so hi*R1 < 2^32
+template <int N>
+__device__ __forceinline__ uint32_t fp_sum64(const uint32_t (&v)[N]) {
+    static_assert(N <= 24, "hi * R1 must fit 32 bits");
+    uint64_t acc = 0;
+#pragma unroll
+    for (int i = 0; i + 2 < N; i += 3) acc += (uint64_t)v[i] + v[i + 1] + v[i + 2];
+#pragma unroll
+    for (int i = N - N % 3; i < N; i++) acc += v[i];
+    uint32_t lo = (uint32_t)acc, hi = (uint32_t)(acc >> 32);
+    lo = addmin(lo, 0u - P, lo); lo = addmin(lo, 0u - P, lo);      // lo < 2^32 < 3p: two corrections
+    uint32_t w = hi * R1;                                          // < 12 * 2^28 < 2p
+    w = addmin(w, 0u - P, w);
+    return fp_add(lo, w);
 }
 
 // external linear layer: circ(2*M4, M4, ..., M4), M4 = [[5,7,1,3],[4,6,1,1],[1,3,5,7],[1,1,4,6]]
@@ -91,6 +119,9 @@ __device__ __forceinline__ void p2_m_int(uint32_t (&c)[24]) {
     a0 = P2_ADD_INT(a0, a1); a2 = P2_ADD_INT(a2, a3); a4 = P2_ADD_INT(a4, a5); a6 = P2_ADD_INT(a6, a7); a8 = P2_ADD_INT(a8, a9); a10 = P2_ADD_INT(a10, a11);
     a0 = P2_ADD_INT(a0, a2); a4 = P2_ADD_INT(a4, a6); a8 = P2_ADD_INT(a8, a10);
     uint32_t s = P2_ADD_INT(P2_ADD_INT(a0, a4), a8);
+#if B200_P2_LAZY & 2
+    s = fp_sum64<24>(c);       // the add tree above is dead code then
+#endif
 #if B200_P2_SHOUP
     // Shoup multiplication by the constant d_i: q = hi(c * d'), r = c*d - q*p in [0, 2p); IMAD.HI + 2 IMAD instead of
     // IMAD.WIDE + IMAD + IMAD.HI (8 instead of 10 multiplier-pipe cycles)
@@ -123,6 +154,49 @@ __device__ __forceinline__ void p2_m_int(uint32_t (&c)[24]) {
 #endif
 #define B200_PRAGMA(x) _Pragma(#x)
 #define B200_UNROLL(n) B200_PRAGMA(unroll n)
+// All 21 internal rounds with cells 1..23 kept lazy in [0, 2p) between rounds (B200_P2_LAZY & 4).  Invariant at the top of a round:
+// c[0] canonical, c[1..23] in [0, 2p), T == sum_{i>=1} c[i] (mod p) canonical.  A Shoup multiply takes any u32, so the lazy cells feed
+// it directly; the new sum is taken over the CORRECTED Shoup outputs plus 23*s.
+#if B200_P2_SHOUP
+__device__ __forceinline__ void p2_internal_rounds_lazy(uint32_t (&c)[24]) {
+    uint32_t T;
+    {
+        uint32_t v[23];
+#pragma unroll
+        for (int i = 0; i < 23; i++) v[i] = c[i + 1];
+        T = fp_sum64<23>(v);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 21; r++) {
+        const uint32_t y = p2_sbox(fp_add(c[0], c_rc[96 + r]));
+        const uint32_t s = fp_add(y, T);                       // sum of the whole state after the S-box
+        uint32_t rr[24];
+        {
+            const uint32_t q = __umulhi(y, c_diag_shoup[0]);
+            uint32_t t = y * c_diag_plain[0] - q * P;
+            rr[0] = addmin(t, 0u - P, t);
+        }
+#pragma unroll
+        for (int i = 1; i < 24; i++) {
+            const uint32_t q = __umulhi(c[i], c_diag_shoup[i]);
+            uint32_t t = c[i] * c_diag_plain[i] - q * P;
+            rr[i] = addmin(t, 0u - P, t);                      // canonical
+        }
+        c[0] = fp_add(rr[0], s);
+#pragma unroll
+        for (int i = 1; i < 24; i++) c[i] = rr[i] + s;         // lazy: < 2p < 2^32
+        // T' = sum_{i>=1} rr[i] + 23 s
+        uint32_t v[23];
+#pragma unroll
+        for (int i = 0; i < 23; i++) v[i] = rr[i + 1];
+        const uint32_t s2 = fp_dbl(s), s4 = fp_dbl(s2), s8 = fp_dbl(s4), s16 = fp_dbl(s8);
+        T = fp_add(fp_sum64<23>(v), fp_add(fp_add(s16, s4), fp_add(s2, s)));
+    }
+#pragma unroll
+    for (int i = 1; i < 24; i++) c[i] = addmin(c[i], 0u - P, c[i]);
+}
+#endif
+
 #ifndef B200_P2_MERGED
 #define B200_P2_MERGED 0
 #endif
@@ -154,11 +228,15 @@ B200_UNROLL(B200_P2_UNROLL_EXT)
         for (int i = 0; i < 24; i++) c[i] = p2_sbox(P2_ADD_RC(c[i], c_rc[24 * r + i]));
         p2_m_ext(c);
     }
+#if (B200_P2_LAZY & 4) && B200_P2_SHOUP
+    p2_internal_rounds_lazy(c);
+#else
 B200_UNROLL(B200_P2_UNROLL_INT)
     for (int r = 0; r < 21; r++) {
         c[0] = p2_sbox(P2_ADD_RC(c[0], c_rc[96 + r]));
         p2_m_int(c);
     }
+#endif
 B200_UNROLL(B200_P2_UNROLL_EXT)
     for (int r = 0; r < 4; r++) {
 #pragma unroll

@@ -51,6 +51,28 @@ int main(int argc, char** argv) {
         printf("%u %u %u %u\n", fp_from_mont(r.c[0]), fp_from_mont(r.c[1]), fp_from_mont(r.c[2]), fp_from_mont(r.c[3]));
         return 0;
     }
-    fprintf(stderr, "usage: device_on_host kat | ops a b | fp4 a0 a1 a2 a3 b0 b1 b2 b3\n");
+    if (argc >= 4 && !strcmp(argv[1], "perms")) {
+        // differential form: `count` permutations of pseudo-random states (plus the all-0 and all-(p-1) states), chained, and one
+        // 64-bit fold of every output word -- two builds of the header that agree here agree on ~24*count field elements
+        uint64_t seed = strtoull(argv[2], 0, 10), fold = 0;
+        const int count = atoi(argv[3]);
+        uint32_t st[24];
+        for (int k = 0; k < count + 2; k++) {
+            for (int i = 0; i < 24; i++) {
+                seed = seed * 6364136223846793005ull + 1442695040888963407ull;
+                st[i] = k == 0 ? 0u : k == 1 ? P - 1 : (uint32_t)((seed >> 33) % P);      // canonical Montgomery words
+            }
+            for (int rep = 0; rep < 3; rep++) {
+                p2_permute(st);
+                for (int i = 0; i < 24; i++) {
+                    if (st[i] >= P) { printf("non-canonical output\n"); return 1; }
+                    fold = (fold ^ st[i]) * 1099511628211ull + (uint64_t)i;
+                }
+            }
+        }
+        printf("%016llx\n", (unsigned long long)fold);
+        return 0;
+    }
+    fprintf(stderr, "usage: device_on_host kat | ops a b | fp4 a0 a1 a2 a3 b0 b1 b2 b3 | perms seed count\n");
     return 2;
 }
