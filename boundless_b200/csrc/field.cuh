@@ -32,7 +32,7 @@ __device__ __forceinline__ uint32_t addmin(uint32_t x, uint32_t y, uint32_t z) {
 #define B200_ADD_V 0
 #endif
 #ifndef B200_REDC_V
-#define B200_REDC_V 3      // measured: +1 % on the Poseidon2 permutation over variant 0 (profiles/microbench_zadd_r01.txt)
+#define B200_REDC_V 4      // the fused form below: 4 instructions per Montgomery multiply instead of 5 (round 2; variant 3 was round 1's)
 #endif
 __device__ __forceinline__ uint32_t fp_add(uint32_t a, uint32_t b) {
 #if B200_ADD_V == 0
@@ -70,9 +70,26 @@ __device__ __forceinline__ uint32_t fp_sub_z(uint32_t a, uint32_t b) {
 __device__ __forceinline__ uint32_t fp_neg(uint32_t a) { return a ? P - a : 0u; }
 __device__ __forceinline__ uint32_t fp_dbl(uint32_t a) { return fp_add(a, a); }
 
+// (T + m*p) >> 32 for T = hi:lo and m = -lo/p mod 2^32, i.e. the whole Montgomery reduction step, as ONE instruction: ptxas fuses the
+// carry-chained pair mad.lo.cc / madc.hi into IMAD.HI.U32 Rd, m, p, T with the 64-bit product T as its addend (the discarded low
+// word is 0 by construction).  Written in C, the same expression leaves a stray IADD3 behind; this form does not (checked in SASS:
+// a Montgomery multiply is IMAD.WIDE + IMAD + IMAD.HI + VIADDMNMX).  Result in [0, T/2^32 + p).
+__device__ __forceinline__ uint32_t fp_redc_step(uint32_t hi, uint32_t lo) {
+    const uint32_t m = lo * (0u - PINV);
+#ifdef B200_HOST_EMULATION
+    return (uint32_t)(((uint64_t)m * P + (((uint64_t)hi << 32) | lo)) >> 32);
+#else
+    uint32_t r, zero;
+    asm("{ mad.lo.cc.u32 %1, %2, %3, %4; madc.hi.u32 %0, %2, %3, %5; }" : "=r"(r), "=r"(zero) : "r"(m), "r"(P), "r"(lo), "r"(hi));
+    return r;
+#endif
+}
 // Montgomery reduction of T < p*2^32 given as (hi, lo): returns T / 2^32 mod p, canonical.
 __device__ __forceinline__ uint32_t fp_redc(uint32_t hi, uint32_t lo) {
-#if B200_REDC_V == 0
+#if B200_REDC_V == 4
+    const uint32_t r = fp_redc_step(hi, lo);     // [0, 2p)
+    return addmin(r, 0u - P, r);
+#elif B200_REDC_V == 0
     uint32_t m = lo * PINV;                 // m*p == lo (mod 2^32)
     uint32_t t = __umulhi(m, P);            // (T - m*p) / 2^32 = hi - t, in (-p, p)
     uint32_t r = hi - t;
@@ -103,13 +120,18 @@ __device__ __forceinline__ uint32_t fp_mul_acc(uint32_t a, uint32_t b, uint64_t 
     uint64_t o = (uint64_t)a * b + acc64;
     return fp_redc((uint32_t)(o >> 32), (uint32_t)o);
 }
-// a*b/2^32 mod p WITHOUT the final correction: the result is in (0, 2p).  Same precondition as fp_mul (a*b < p*2^32).  A lazy value
-// may feed ONE side of a following fp_mul / Shoup multiply (those take any u32 on one side), never an add.
+// a*b/2^32 mod p WITHOUT the final correction.  Same precondition as fp_mul (a*b < p*2^32); the result is in [0, a*b/2^32 + p), i.e.
+// below 1.47p for canonical a, b and below 2p always.  A lazy value may feed ONE side of a following fp_mul / Shoup multiply (the
+// other side canonical keeps the product below p*2^32), never an add.
 __device__ __forceinline__ uint32_t fp_mul_lazy(uint32_t a, uint32_t b) {
     uint64_t o = (uint64_t)a * b;
+#if B200_REDC_V == 4
+    return fp_redc_step((uint32_t)(o >> 32), (uint32_t)o);
+#else
     uint32_t m = (uint32_t)o * PINV;
     uint32_t t = __umulhi(m, P);
     return (uint32_t)(o >> 32) - t + P;      // (-p, p) + p, one three-input add
+#endif
 }
 __device__ __forceinline__ uint32_t fp_sqr(uint32_t a) { return fp_mul(a, a); }
 __device__ __forceinline__ uint32_t fp_to_mont(uint32_t x) { return fp_mul(x, R2); }      // x < p

@@ -66,21 +66,26 @@ __device__ __forceinline__ uint32_t p2_sbox(uint32_t x) {
 #endif
     return fp_mul(x3, x4);
 }
-// sum of `n` canonical values taken in 64 bits (no per-term correction), reduced once: acc = hi*2^32 + lo == hi*R1 + lo (mod p),
-// hi <= n*p/2^32 < 12 for n <= 24, so hi*R1 < 2^32
+// V mod p for a 64-bit V < 2^38 (sums of up to ~100 field elements): q = floor((V >> 8) * floor(2^40 / p) / 2^32) is floor(V / p) or
+// one less (the constant 546 is 0.99976 of 2^40 / p and V / p < 128, so the estimate falls short by less than 1), hence
+// V - q*p is in [0, 2p), fits 32 bits, and one correction makes it canonical.  SHF + IMAD.HI + IMAD + VIADDMNMX.
+__device__ __forceinline__ uint32_t fp_reduce38(uint64_t v) {
+    const uint32_t q = __umulhi((uint32_t)(v >> 8), 546u);
+    const uint32_t r = (uint32_t)v - q * P;
+    return addmin(r, 0u - P, r);
+}
+// sum of N canonical values (+ a 64-bit starting value) without per-term corrections: two canonical values add without a carry
+// (2p < 2^32), the pair sums are accumulated in 64 bits, the total is reduced once.  acc0 + N*p must stay below 2^38.
 template <int N>
-__device__ __forceinline__ uint32_t fp_sum64(const uint32_t (&v)[N]) {
-    static_assert(N <= 24, "hi * R1 must fit 32 bits");
-    uint64_t acc = 0;
+__device__ __forceinline__ uint32_t fp_sum64(const uint32_t (&v)[N], uint64_t acc0 = 0) {
+    static_assert(N <= 64, "total must stay below 2^38");
+    uint64_t acc = acc0;
 #pragma unroll
-    for (int i = 0; i + 2 < N; i += 3) acc += (uint64_t)v[i] + v[i + 1] + v[i + 2];
-#pragma unroll
-    for (int i = N - N % 3; i < N; i++) acc += v[i];
-    uint32_t lo = (uint32_t)acc, hi = (uint32_t)(acc >> 32);
-    lo = addmin(lo, 0u - P, lo); lo = addmin(lo, 0u - P, lo);      // lo < 2^32 < 3p: two corrections
-    uint32_t w = hi * R1;                                          // < 12 * 2^28 < 2p
-    w = addmin(w, 0u - P, w);
-    return fp_add(lo, w);
+    for (int i = 0; i + 3 < N; i += 4) acc += (uint64_t)(v[i] + v[i + 1]) + (uint64_t)(v[i + 2] + v[i + 3]);
+    if ((N & 3) == 3) acc += (uint64_t)(v[N - 3] + v[N - 2]) + (uint64_t)v[N - 1];
+    else if ((N & 3) == 2) acc += (uint64_t)(v[N - 2] + v[N - 1]);
+    else if ((N & 3) == 1) acc += (uint64_t)v[N - 1];
+    return fp_reduce38(acc);
 }
 
 // external linear layer: circ(2*M4, M4, ..., M4), M4 = [[5,7,1,3],[4,6,1,1],[1,3,5,7],[1,1,4,6]]
@@ -156,7 +161,8 @@ __device__ __forceinline__ void p2_m_int(uint32_t (&c)[24]) {
 #define B200_UNROLL(n) B200_PRAGMA(unroll n)
 // All 21 internal rounds with cells 1..23 kept lazy in [0, 2p) between rounds (B200_P2_LAZY & 4).  Invariant at the top of a round:
 // c[0] canonical, c[1..23] in [0, 2p), T == sum_{i>=1} c[i] (mod p) canonical.  A Shoup multiply takes any u32, so the lazy cells feed
-// it directly; the new sum is taken over the CORRECTED Shoup outputs plus 23*s.
+// it directly and the "+ s" needs no correction (one instruction less per cell and round); the next T is the sum of the CORRECTED
+// Shoup outputs plus 23*s, taken in 64 bits (23*s is the IMAD.WIDE that starts the accumulator) and reduced once.
 #if B200_P2_SHOUP
 __device__ __forceinline__ void p2_internal_rounds_lazy(uint32_t (&c)[24]) {
     uint32_t T;
@@ -170,30 +176,72 @@ __device__ __forceinline__ void p2_internal_rounds_lazy(uint32_t (&c)[24]) {
     for (int r = 0; r < 21; r++) {
         const uint32_t y = p2_sbox(fp_add(c[0], c_rc[96 + r]));
         const uint32_t s = fp_add(y, T);                       // sum of the whole state after the S-box
-        uint32_t rr[24];
+        uint32_t rr[23];
         {
             const uint32_t q = __umulhi(y, c_diag_shoup[0]);
             uint32_t t = y * c_diag_plain[0] - q * P;
-            rr[0] = addmin(t, 0u - P, t);
+            t = addmin(t, 0u - P, t);
+            c[0] = fp_add(t, s);
         }
 #pragma unroll
         for (int i = 1; i < 24; i++) {
             const uint32_t q = __umulhi(c[i], c_diag_shoup[i]);
-            uint32_t t = c[i] * c_diag_plain[i] - q * P;
-            rr[i] = addmin(t, 0u - P, t);                      // canonical
+            const uint32_t t = c[i] * c_diag_plain[i] - q * P;
+            rr[i - 1] = addmin(t, 0u - P, t);                  // canonical
+            c[i] = rr[i - 1] + s;                              // lazy: < 2p < 2^32
         }
-        c[0] = fp_add(rr[0], s);
-#pragma unroll
-        for (int i = 1; i < 24; i++) c[i] = rr[i] + s;         // lazy: < 2p < 2^32
-        // T' = sum_{i>=1} rr[i] + 23 s
-        uint32_t v[23];
-#pragma unroll
-        for (int i = 0; i < 23; i++) v[i] = rr[i + 1];
-        const uint32_t s2 = fp_dbl(s), s4 = fp_dbl(s2), s8 = fp_dbl(s4), s16 = fp_dbl(s8);
-        T = fp_add(fp_sum64<23>(v), fp_add(fp_add(s16, s4), fp_add(s2, s)));
+        T = fp_sum64<23>(rr, (uint64_t)s * 23u);               // < 46p
     }
 #pragma unroll
     for (int i = 1; i < 24; i++) c[i] = addmin(c[i], 0u - P, c[i]);
+}
+#endif
+
+// Hybrid form of the 21 internal rounds (B200_P2_NMACC = K in 1..24): cells 0..K-1 are updated as ONE Montgomery multiply-accumulate
+// REDC(diag_i * c_i + X), X == s * 2^32 (mod p) with hi(X) < p/2 riding in the IMAD.WIDE accumulator (4 instructions, 10
+// multiplier-pipe cycles, canonical result), cells K..23 as in p2_internal_rounds_lazy (Shoup multiply, 5 instructions, 8 cycles,
+// lazy result).  K trades multiplier-pipe cycles for instruction count; the best K is a measurement (tools/microbench.cu).
+// Invariant at the top of a round: c[0..K-1] canonical, c[K..23] in [0, 2p), T == sum_{i>=1} c[i] (mod p) canonical.
+#ifndef B200_P2_NMACC
+#define B200_P2_NMACC 0
+#endif
+#if B200_P2_NMACC > 0
+__device__ __forceinline__ void p2_internal_rounds_hybrid(uint32_t (&c)[24]) {
+    constexpr int K = B200_P2_NMACC;
+    constexpr uint32_t HALF = (P + 1) / 2;
+    uint32_t T;
+    {
+        uint32_t v[23];
+#pragma unroll
+        for (int i = 0; i < 23; i++) v[i] = c[i + 1];
+        T = fp_sum64<23>(v);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 21; r++) {
+        const uint32_t y = p2_sbox(fp_add(c[0], c_rc[96 + r]));
+        const uint32_t s = fp_add(y, T);
+        // X = s << 32 when s < (p+1)/2, else (2s - p) << 31 = {hi: s - (p+1)/2, lo: 2^31}: both are s * 2^32 mod p
+        const uint32_t xhi = addmin(s, 0u - HALF, s);
+        const uint32_t xlo = (s - xhi) << 31;                  // (p+1)/2 is odd
+        const uint64_t X = ((uint64_t)xhi << 32) | xlo;
+        uint32_t o[23];                                        // canonical summands of the next T
+        c[0] = fp_mul_acc(c_diag[0], y, X);
+#pragma unroll
+        for (int i = 1; i < 24; i++) {
+            if (i < K) {
+                c[i] = fp_mul_acc(c_diag[i], c[i], X);
+                o[i - 1] = c[i];
+            } else {
+                const uint32_t q = __umulhi(c[i], c_diag_shoup[i]);
+                const uint32_t t = c[i] * c_diag_plain[i] - q * P;
+                o[i - 1] = addmin(t, 0u - P, t);
+                c[i] = o[i - 1] + s;
+            }
+        }
+        T = fp_sum64<23>(o, (uint64_t)s * (uint32_t)(24 - (K > 1 ? K : 1)));
+    }
+#pragma unroll
+    for (int i = (K > 1 ? K : 1); i < 24; i++) c[i] = addmin(c[i], 0u - P, c[i]);
 }
 #endif
 
@@ -228,7 +276,9 @@ B200_UNROLL(B200_P2_UNROLL_EXT)
         for (int i = 0; i < 24; i++) c[i] = p2_sbox(P2_ADD_RC(c[i], c_rc[24 * r + i]));
         p2_m_ext(c);
     }
-#if (B200_P2_LAZY & 4) && B200_P2_SHOUP
+#if B200_P2_NMACC > 0
+    p2_internal_rounds_hybrid(c);
+#elif (B200_P2_LAZY & 4) && B200_P2_SHOUP
     p2_internal_rounds_lazy(c);
 #else
 B200_UNROLL(B200_P2_UNROLL_INT)

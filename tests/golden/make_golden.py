@@ -55,6 +55,17 @@ def main():
     d = o.seal_digest(g["seal_po2_9"])
     g["seal_digest_po2_9"] = d
     g["lift_sha"] = sha(o.prove(10, int(d[0]) | (int(d[1]) << 32), 16, 128, 16, kind=1, input_digest=d))
+    # BASELINE-size seals: segments at po2 16 / 18 / 20 (seed 0xB2000000 + po2, 16/208/32), and lift + join at the
+    # recursion size po2 18 (16/128/16) over two po2-12 segments (indices 40, 41).  Minutes of CPU; sha256 only.
+    for po2 in (16, 18, 20):
+        g["seal_sha_po2_%d" % po2] = sha(o.prove(po2, 0xB2000000 + po2))
+    lifts = []
+    for i in range(2):
+        d = o.seal_digest(o.prove(12, 0xB2000000 + 40 + i))
+        lifts.append(o.prove(18, int(d[0]) | (int(d[1]) << 32), 16, 128, 16, kind=1, input_digest=d))
+        g["lift18_sha_%d" % i] = sha(lifts[i])
+    d = o.hash_pair(o.seal_digest(lifts[0]), o.seal_digest(lifts[1]))
+    g["join18_sha"] = sha(o.prove(18, int(d[0]) | (int(d[1]) << 32), 16, 128, 16, kind=2, input_digest=d))
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.npz")
     np.savez_compressed(out, **g)
     print("wrote", out, os.path.getsize(out), "bytes")

@@ -177,6 +177,24 @@ def test_commit_group(gpu, b200lib, oracle, lg_n, count):
     assert np.array_equal(host(d_n)[8:], nodes[8:])        # node 0 is unused
 
 
+def test_commit_group_headline_size(gpu, b200lib, oracle):
+    """commit_group at N = 2^20: iNTT + zk_shift, expand + NTT to 2^22, 2^22 leaves, the whole tree -- every
+    word of coefficients, evaluations and nodes against the oracle."""
+    torch = gpu
+    lg_n, count = 20, 16
+    g = torch.Generator(device="cuda"); g.manual_seed(2020)
+    d_c = torch.randint(0, 2013265921, (count << lg_n,), dtype=torch.int32, device="cuda", generator=g)
+    a = host(d_c).copy()
+    d_e = torch.zeros(count << (lg_n + 2), dtype=torch.int32, device="cuda")
+    d_n = torch.zeros(2 * (1 << (lg_n + 2)) * 8, dtype=torch.int32, device="cuda")
+    ck(b200lib.b200_commit_group(ptr(d_c), ptr(d_e), ptr(d_n), lg_n, count, None))
+    torch.cuda.synchronize()
+    co, ev, nodes = oracle.commit_group(a, lg_n, count)
+    assert np.array_equal(host(d_c), co)
+    assert np.array_equal(host(d_e), ev)
+    assert np.array_equal(host(d_n)[8:], nodes[8:])
+
+
 def test_full_size_deep_pipeline_properties(gpu, b200lib, oracle):
     """BASELINE size (N = 2^20): mix 272 columns into 3 combos, divide each by (x - z), sum: size-independent checks --
     the remainder equals the combo evaluated by b200_batch_evaluate_any-style Horner on a strided sample is too slow on the

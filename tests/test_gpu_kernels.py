@@ -239,3 +239,69 @@ def test_stream_argument(gpu, b200lib, oracle):
     ck(b200lib.b200_batch_intt(ptr(d), 12, 4, C.c_void_p(s.cuda_stream)))
     s.synchronize()
     assert np.array_equal(host(d), oracle.batch_intt(a, 12, 4))
+
+
+# ---- BASELINE-size cases (VERDICT r01 "Next round" item 1): the shapes the headline runs, bit-exact against the oracle ----------------
+def dev_rand(torch, n, seed):
+    """n canonical Montgomery words generated on the device (any value below p is a valid element); host copy for the oracle"""
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    t = torch.randint(0, P, (n,), dtype=torch.int32, device="cuda", generator=g)
+    return t, t.cpu().numpy().view(np.uint32)
+
+
+def test_poseidon2_rows_full_data_group(gpu, b200lib, oracle):
+    """K4 at the headline shape: 2^22 rows x 208 columns (the data group of a 2^20-row segment, 13 permutations per row)."""
+    torch = gpu
+    rows, cols = 1 << 22, 208
+    d_m, m = dev_rand(torch, rows * cols, 2208)
+    d_out = torch.zeros(rows * 8, dtype=torch.int32, device="cuda")
+    ck(b200lib.b200_poseidon2_rows(ptr(d_out), ptr(d_m), rows, cols, None))
+    torch.cuda.synchronize()
+    got = host(d_out)
+    del d_m, d_out
+    assert np.array_equal(got, oracle.hash_rows(m, rows, cols))
+
+
+def test_merkle_tree_full_size(gpu, b200lib, oracle):
+    """K4 + K5 at 2^22 leaves (every layer kernel of the headline tree: wide folds, the one-CTA top, the warp-form last six layers)."""
+    torch = gpu
+    lg_rows, cols = 22, 16
+    rows = 1 << lg_rows
+    d_m, m = dev_rand(torch, rows * cols, 2216)
+    d_nodes = torch.zeros(2 * rows * 8, dtype=torch.int32, device="cuda")
+    ck(b200lib.b200_merkle_tree(ptr(d_nodes), ptr(d_m), lg_rows, cols, None))
+    torch.cuda.synchronize()
+    ref = oracle.merkle_build(m, rows, cols)
+    assert np.array_equal(host(d_nodes)[8:], ref[8:])
+
+
+@pytest.mark.parametrize("count", [16, 272])
+def test_batch_expand_ntt_full_size(gpu, b200lib, oracle, count):
+    """K3 at the headline shape: 2^20 coefficients -> 2^22 evaluations, 16 columns (one launch group) and all 272 columns of a segment."""
+    torch = gpu
+    lg_n = 20
+    d_in, a = dev_rand(torch, count << lg_n, 2000 + count)
+    d_out = torch.zeros(count << (lg_n + 2), dtype=torch.int32, device="cuda")
+    ck(b200lib.b200_batch_expand_ntt(ptr(d_out), ptr(d_in), lg_n, 2, count, None))
+    torch.cuda.synchronize()
+    got = host(d_out)
+    del d_in, d_out
+    assert np.array_equal(got, oracle.batch_expand_ntt(a, lg_n, count, 2))
+
+
+@pytest.mark.parametrize("lg_n,count", [(20, 272), (22, 4), (23, 2), (24, 2)])
+def test_batch_intt_large_against_the_oracle(gpu, b200lib, oracle, lg_n, count):
+    """K1 (+K2 fused) against the oracle at the headline shape (272 x 2^20) and at lg_n 22-24 (the check-polynomial iNTT is 2^22;
+    upstream MAX_CYCLES_PO2 = 24), not only as a round trip."""
+    torch = gpu
+    d, a = dev_rand(torch, count << lg_n, 100 * lg_n + count)
+    d2 = d.clone()
+    ck(b200lib.b200_batch_intt(ptr(d), lg_n, count, None))
+    ck(b200lib.b200_batch_intt_zk_shift(ptr(d2), lg_n, count, None))
+    torch.cuda.synchronize()
+    ref = oracle.batch_intt(a, lg_n, count)
+    assert np.array_equal(host(d), ref)
+    assert np.array_equal(host(d2), oracle.batch_zk_shift(ref, lg_n, count))
+    ck(b200lib.b200_batch_ntt(ptr(d), lg_n, count, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(host(d), a)
