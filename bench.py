@@ -196,6 +196,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--slots", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-job-records", action="store_true", help="skip the config 3 (queue) and config 4 (tree) sub-records")
     ap.add_argument("--mode", default="segments", choices=["segments", "tree"],
                     help="segments: BASELINE configs 2/3 (default, the contract line); tree: config 4, prove+lift+join to one root")
     ap.add_argument("--segments-per-gpu", type=int, default=4, help="tree mode: segments per rank")
@@ -235,37 +236,79 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    if args.mode == "tree":
-        # BASELINE config 4: every rank proves + lifts its block, the Planner-shaped join DAG runs across ranks (NCCL
-        # send/recv of ~0.1 MB receipts), one root STARK lands on rank 0.
-        from boundless_b200 import VerifierContext
-        from boundless_b200.dist import prove_job
-        from boundless_b200.prover_server import KIND_LIFT, SuccinctReceipt
-        n_seg = args.segments_per_gpu * world
-        ctx = VerifierContext()
-        rec_words = srv.seal_words(srv._rec_circuit(KIND_LIFT))
-        def prove_and_lift(i):
-            return srv.lift(srv.prove_segment(ctx, Segment(index=i, po2=PO2)))
-        prove_job(min(world, 2) * 1, prove_and_lift, srv.join, lambda r: r.seal, lambda sl, c: SuccinctReceipt(sl, 2, c), rec_words,
-                  device=torch.device("cuda", local_rank))          # warm-up job
+    def tree_record(segs_per_gpu):
+        """BASELINE config 4: segs_per_gpu x world segments -> prove + verify + lift + verify (tasks/prove.rs:44-108, one enqueue each)
+        -> the reference Planner's join DAG (verify, verify, join, verify per join: tasks/join.rs:41-79) -> ONE root receipt on rank 0.
+        dist.JobRunner keeps every slot of every GPU busy, launches a join the moment both inputs exist, keeps receipts in device
+        memory and moves the cross-GPU ones as device tensors over NCCL (announced by a gloo control message).  Wall clock, barrier to
+        barrier, max over ranks; the root is read back and checked by the device verifier on rank 0 outside the timed region."""
+        from boundless_b200.dist import B200Engine, JobRunner
+        dev = torch.device("cuda", local_rank)
+        eng = B200Engine(srv, lambda i: Segment(index=i, po2=PO2), dev, verify=True)
+        JobRunner(eng, 2 * world).run()                      # warm-up: NCCL point-to-point channels, the gloo control group, buffers
+        n_seg = segs_per_gpu * world
         barrier()
         t0 = time.perf_counter()
-        root, stats = prove_job(n_seg, prove_and_lift, srv.join, lambda r: r.seal, lambda sl, c: SuccinctReceipt(sl, 2, c), rec_words,
-                                device=torch.device("cuda", local_rank),
-                                prove_and_lift_many=lambda idx: srv.prove_and_lift_many([Segment(index=i, po2=PO2) for i in idx]))
+        root, stats = JobRunner(eng, n_seg).run()
         barrier()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt, float(stats["bytes_sent"])], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([dt, float(stats["bytes_sent"]), float(stats["sent"]), float(stats["max_in_flight"])], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt[0:1], op=dist.ReduceOp.MAX)
-            dist.all_reduce(tt[1:2], op=dist.ReduceOp.SUM)
+            dist.all_reduce(tt[1:3], op=dist.ReduceOp.SUM)
+            dist.all_reduce(tt[3:4], op=dist.ReduceOp.MAX)
+        if rank != 0:
+            return None
+        from boundless_b200.prover_server import KIND_JOIN, KIND_LIFT
+        srv.verify_integrity(root)                            # raises unless the root seal is a valid join / lift receipt
+        return {"segments": n_seg, "segments_per_gpu": segs_per_gpu, "ms_to_root": float(tt[0]) * 1e3,
+                "segments_per_sec_to_root": n_seg / float(tt[0]), "joins": n_seg - 1, "lifts": n_seg,
+                "nccl_bytes_moved": int(tt[1]), "nccl_transfers": int(tt[2]), "max_tasks_in_flight_per_gpu": int(tt[3]),
+                "root_claim": list(root.claim), "root_kind": "join" if root.kind == KIND_JOIN else "lift", "root_verifies": True,
+                "verify_after_every_step": True, "recursion_po2": srv.opts.recursion_po2,
+                "exchange": "device tensors, torch.distributed isend/irecv (NCCL) announced over a gloo control group; no host bounce",
+                "timer": "wall clock barrier-to-barrier, max over ranks"}
+
+    def queue_record(n_per_gpu):
+        """BASELINE config 3 "via the queue": n_per_gpu x world Prove tasks created by the executor stand-in in a taskdb (one queue per
+        GPU process; segment i belongs to rank i mod world), claimed by the agent loop in the reference's (priority, creation)
+        order with `slots` claims in flight (tasks.poll_work_pipelined).  Every claim runs the whole Prove task: prove_segment ->
+        verify_integrity -> lift -> verify_integrity -> store the lifted receipt -> done (tasks/prove.rs:17-129)."""
+        from boundless_b200 import tasks, wire
+        from boundless_b200.taskdb import MemoryTaskDb
+        db = MemoryTaskDb()
+        db.create_stream(wire.PROVE_WORK_TYPE, user_id="u"); db.create_stream(wire.AUX_WORK_TYPE, user_id="u")
+        db.create_stream(wire.JOIN_WORK_TYPE, user_id="u")    # JOIN_STREAM mode (executor.rs:517-525): the prove stream carries Prove tasks only
+        execs = db.create_stream(wire.EXEC_WORK_TYPE, user_id="u")
+        store = tasks.MemoryHotStore()
+        n_total = n_per_gpu * world
+        store.set_bytes("input:q", json.dumps({"segments": n_per_gpu, "po2": PO2, "seed_base": 0xB2000000 + 70000 + rank * n_per_gpu}).encode())
+        job = db.create_job(execs, wire.task_type_to_value(wire.ExecutorReq(image="ab" * 32, input="input:q", user_id="u")), user_id="u")
+        tasks.poll_work(tasks.Agent(db, store, None, tasks.AgentArgs(task_stream=wire.EXEC_WORK_TYPE, segment_po2=PO2, join_stream=True)))
+        agent = tasks.Agent(db, store, srv, tasks.AgentArgs(task_stream=wire.PROVE_WORK_TYPE, segment_po2=PO2))
+        barrier()
+        t0 = time.perf_counter()
+        claimed = tasks.poll_work_pipelined(agent)           # until the prove stream is empty
+        barrier()
+        dt = time.perf_counter() - t0
+        ok = agent.errors == [] and claimed == n_per_gpu and len(agent.processed) == n_per_gpu and db.job_state(job) == "running"
+        tt = torch.tensor([dt, float(ok)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt[0:1], op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt[1:2], op=dist.ReduceOp.MIN)
+        return {"segments": n_total, "prove_tasks_per_gpu": n_per_gpu, "segments_per_sec": n_total / float(tt[0]), "ms_total": float(tt[0]) * 1e3,
+                "all_tasks_done": bool(float(tt[1]) == 1.0), "claims_in_flight": slots,
+                "task_body": "prove_segment + verify_integrity + lift (po2 %d) + verify_integrity + store, per claim" % srv.opts.recursion_po2,
+                "queue": "taskdb.MemoryTaskDb per GPU process, claims via tasks.poll_work_pipelined (priority, creation order)",
+                "timer": "wall clock barrier-to-barrier, max over ranks"}
+
+    if args.mode == "tree":
+        rec = tree_record(args.segments_per_gpu)
         if rank == 0:
-            out = {"metric": "job_segments_per_sec_to_root", "value": n_seg / float(tt[0]), "unit": "segments/s", "n_gpus": world,
-                   "steps": 1, "warmup": 1, "ms_per_step": float(tt[0]) * 1e3, "higher_is_better": True, "scaling": "weak",
+            out = {"metric": "job_segments_per_sec_to_root", "value": rec["segments_per_sec_to_root"], "unit": "segments/s", "n_gpus": world,
+                   "steps": 1, "warmup": 1, "ms_per_step": rec["ms_to_root"], "higher_is_better": True, "scaling": "weak",
                    "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-                   "config": {"workload": "config 4: %d x 1M-cycle segments -> prove + lift (po2 18) -> join tree -> one root" % n_seg,
-                              "segments": n_seg, "root_claim": list(root.claim), "nccl_bytes_moved": int(tt[1]),
-                              "joins": n_seg - 1, "timer": "wall clock sync-to-sync, max over ranks"}}
+                   "config": dict(rec, workload="config 4: %d x 1M-cycle segments -> prove + lift (po2 18) -> join tree -> one root" % rec["segments"])}
             sys.stdout.flush(); os.dup2(real_stdout, 1); print(json.dumps(out), flush=True); os.dup2(2, 1)
         srv.close()
         if world > 1:
@@ -340,6 +383,10 @@ def main():
     e2e_value = world * args.steps / float(te[0])      # wall clock sync-to-sync: includes H2D, launches, D2H
     seal_bytes = int(rec_e.seal.size * 4)
 
+    # ---- BASELINE configs 3 and 4 as sub-records of the same line (every rank takes part) ----
+    queue = None if args.no_job_records else queue_record(max(4, min(args.steps, 16)))
+    tree = None if args.no_job_records else tree_record(args.segments_per_gpu)
+
     out = None
     if rank == 0:
         roof, roof_int, kernels = kernel_roofline(torch, L, pk)
@@ -359,6 +406,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof, "roofline_int32": roof_int, "kernels": kernels,
+            "queue": queue, "tree": tree,
         }
         if not args.no_cpu_baseline and world == 1:
             os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)

@@ -95,13 +95,18 @@ __global__ void __launch_bounds__(1024, 1) k_p2_fold_top_w(uint32_t* nodes, uint
 cudaError_t launch_poseidon2_rows(uint32_t* d_out, const uint32_t* d_matrix, uint32_t rows, uint32_t cols, size_t col_stride,
                                   cudaStream_t s) {
     if (rows == 0) return cudaSuccess;
-    static const int cfg = getenv("B200_P2_CFG") ? atoi(getenv("B200_P2_CFG")) : 0;      // launch-shape A/B switch (tools/time_p2.py)
+    // launch-shape A/B switch (tools/time_p2_variants.py).  Default <256, 4>: 48 registers -> 5 CTAs = 40 warps per SM, measured best for
+    // the round-2 arithmetic (profiles/p2_variants_r02.txt: 23.5 ms for 2^22 x 208 against 23.9 ms with <256, 2>; 40-register shapes lose)
+    static const int cfg = getenv("B200_P2_CFG") ? atoi(getenv("B200_P2_CFG")) : 1;
     switch (cfg) {
-        case 1: B200_LAUNCH(k_p2_rows<256, 4>)<<<(rows + 255) / 256, 256, 0, s>>>(d_out, d_matrix, rows, cols, col_stride); break;
+        case 0: B200_LAUNCH(k_p2_rows<256, 2>)<<<(rows + 255) / 256, 256, 0, s>>>(d_out, d_matrix, rows, cols, col_stride); break;
         case 2: B200_LAUNCH(k_p2_rows<512, 2>)<<<(rows + 511) / 512, 512, 0, s>>>(d_out, d_matrix, rows, cols, col_stride); break;
         case 3: B200_LAUNCH(k_p2_rows<1024, 1>)<<<(rows + 1023) / 1024, 1024, 0, s>>>(d_out, d_matrix, rows, cols, col_stride); break;
         case 4: B200_LAUNCH(k_p2_rows<128, 4>)<<<(rows + 127) / 128, 128, 0, s>>>(d_out, d_matrix, rows, cols, col_stride); break;
-        default: B200_LAUNCH(k_p2_rows<256, 2>)<<<(rows + 255) / 256, 256, 0, s>>>(d_out, d_matrix, rows, cols, col_stride); break;
+        case 5: B200_LAUNCH(k_p2_rows<256, 6>)<<<(rows + 255) / 256, 256, 0, s>>>(d_out, d_matrix, rows, cols, col_stride); break;
+        case 6: B200_LAUNCH(k_p2_rows<128, 12>)<<<(rows + 127) / 128, 128, 0, s>>>(d_out, d_matrix, rows, cols, col_stride); break;
+        case 7: B200_LAUNCH(k_p2_rows<256, 5>)<<<(rows + 255) / 256, 256, 0, s>>>(d_out, d_matrix, rows, cols, col_stride); break;
+        default: B200_LAUNCH(k_p2_rows<256, 4>)<<<(rows + 255) / 256, 256, 0, s>>>(d_out, d_matrix, rows, cols, col_stride); break;
     }
     return cudaGetLastError();
 }

@@ -139,6 +139,9 @@ struct VerifyShape {
 };
 cudaError_t launch_verify_reset(uint32_t* ctx, cudaStream_t s);
 cudaError_t launch_verify_canonical(uint32_t* ctx, const uint32_t* seal, uint32_t words, cudaStream_t s);
+// seal[0..5) must be the circuit the caller expects, seal[5..8) zero: else verdict 103
+cudaError_t launch_verify_header(uint32_t* ctx, const uint32_t* seal, uint32_t po2, uint32_t w_code, uint32_t w_data, uint32_t w_accum,
+                                 uint32_t kind, cudaStream_t s);
 cudaError_t launch_verify_fold_top(uint32_t* root_out, const uint32_t* top, uint32_t top_size, cudaStream_t s);
 cudaError_t launch_verify_constraint(uint32_t* ctx, const uint32_t* u, const uint32_t* pm, const uint32_t* z, uint32_t w_code,
                                      uint32_t w_data, uint32_t w_accum, cudaStream_t s);

@@ -28,8 +28,15 @@ static __constant__ uint32_t c_diag_shoup[24] = B200_P2_DIAG_SHOUP_INIT;   // fl
 
 // fp_add written so that ptxas cannot encode the sum as IMAD.IADD (multiplier pipe): both halves are VIADDMNMX (ALU pipe).
 // Which adds of the linear layers use it is a measured trade-off (B200_P2_V, tools/microbench.cu).
+#ifndef B200_P2_ZALL
+#define B200_P2_ZALL 1
+#endif
 #ifndef B200_P2_V
+#if B200_P2_ZALL
+#define B200_P2_V 63
+#else
 #define B200_P2_V 0
+#endif
 #endif
 __device__ __forceinline__ uint32_t fp_add_alu(uint32_t a, uint32_t b) {
     uint32_t s = addmin(a, b, 0xffffffffu);
@@ -45,8 +52,20 @@ __device__ __forceinline__ uint32_t fp_add_alu(uint32_t a, uint32_t b) {
 #define P2_ADD_SUM(a, b) ((B200_P2_Z & 2) ? fp_add_z(a, b) : (B200_P2_V & 2) ? fp_add_alu(a, b) : fp_add(a, b))
 #define P2_ADD_FIN(a, b) ((B200_P2_Z & 4) ? fp_add_z(a, b) : (B200_P2_V & 4) ? fp_add_alu(a, b) : fp_add(a, b))
 #define P2_ADD_INT(a, b) ((B200_P2_Z & 8) ? fp_add_z(a, b) : (B200_P2_V & 8) ? fp_add_alu(a, b) : fp_add(a, b))
-#define P2_ADD_RC(a, b)  ((B200_P2_Z & 16) ? fp_add_z(a, b) : fp_add(a, b))
-#define P2_ADD_IS(a, b)  ((B200_P2_Z & 32) ? fp_add_z(a, b) : fp_add(a, b))
+#define P2_ADD_RC(a, b)  ((B200_P2_Z & 16) ? fp_add_z(a, b) : (B200_P2_V & 16) ? fp_add_alu(a, b) : fp_add(a, b))
+#define P2_ADD_IS(a, b)  ((B200_P2_Z & 32) ? fp_add_z(a, b) : (B200_P2_V & 32) ? fp_add_alu(a, b) : fp_add(a, b))
+// B200_P2_ZALL: EVERY plain 32-bit add of the permutation is a VIADDMNMX (min(a + b, 2^32 - 1) == a + b), an ALU-pipe-only instruction,
+// so that the multiplier pipe -- the unit that binds this kernel (ncu: fmaheavy 92 % busy, ALU 60 %) -- carries multiplies only.  Forcing
+// a subset does nothing (ptxas re-balances by encoding OTHER adds as IMAD.IADD), three-input adds with a runtime zero get re-associated
+// back into two-input ones, and with round 1's instruction mix forcing all adds overloaded the ALU pipe instead
+// (profiles/microbench_zadd_r01.txt); with the fused reduction and the lazy internal rounds the ALU pipe has the room.
+#if B200_P2_ZALL
+__device__ __forceinline__ uint32_t p2_add32(uint32_t a, uint32_t b) { return addmin(a, b, 0xffffffffu); }
+__device__ __forceinline__ uint32_t p2_fp_add(uint32_t a, uint32_t b) { return fp_add_alu(a, b); }
+#else
+__device__ __forceinline__ uint32_t p2_add32(uint32_t a, uint32_t b) { return a + b; }
+__device__ __forceinline__ uint32_t p2_fp_add(uint32_t a, uint32_t b) { return fp_add(a, b); }
+#endif
 
 // B200_P2_LAZY: instruction-count variants prepared for measurement (arithmetic checked on the host by
 // tests/test_device_code_on_host.py).  Bitmask:
@@ -54,7 +73,7 @@ __device__ __forceinline__ uint32_t fp_add_alu(uint32_t a, uint32_t b) {
 //   2  internal layer: the 24-term sum is taken in 64 bits and reduced once                              (~ -10 per round)
 //   4  internal rounds: cells 1..23 stay lazy in [0, 2p) between rounds, the sum is carried along        (~ -7 per round)
 #ifndef B200_P2_LAZY
-#define B200_P2_LAZY 0
+#define B200_P2_LAZY 7
 #endif
 __device__ __forceinline__ uint32_t p2_sbox(uint32_t x) {
     uint32_t x2 = fp_mul(x, x);
@@ -81,9 +100,9 @@ __device__ __forceinline__ uint32_t fp_sum64(const uint32_t (&v)[N], uint64_t ac
     static_assert(N <= 64, "total must stay below 2^38");
     uint64_t acc = acc0;
 #pragma unroll
-    for (int i = 0; i + 3 < N; i += 4) acc += (uint64_t)(v[i] + v[i + 1]) + (uint64_t)(v[i + 2] + v[i + 3]);
-    if ((N & 3) == 3) acc += (uint64_t)(v[N - 3] + v[N - 2]) + (uint64_t)v[N - 1];
-    else if ((N & 3) == 2) acc += (uint64_t)(v[N - 2] + v[N - 1]);
+    for (int i = 0; i + 3 < N; i += 4) acc += (uint64_t)p2_add32(v[i], v[i + 1]) + (uint64_t)p2_add32(v[i + 2], v[i + 3]);
+    if ((N & 3) == 3) acc += (uint64_t)p2_add32(v[N - 3], v[N - 2]) + (uint64_t)v[N - 1];
+    else if ((N & 3) == 2) acc += (uint64_t)p2_add32(v[N - 2], v[N - 1]);
     else if ((N & 3) == 1) acc += (uint64_t)v[N - 1];
     return fp_reduce38(acc);
 }
@@ -174,21 +193,21 @@ __device__ __forceinline__ void p2_internal_rounds_lazy(uint32_t (&c)[24]) {
     }
 #pragma unroll 1
     for (int r = 0; r < 21; r++) {
-        const uint32_t y = p2_sbox(fp_add(c[0], c_rc[96 + r]));
-        const uint32_t s = fp_add(y, T);                       // sum of the whole state after the S-box
+        const uint32_t y = p2_sbox(p2_fp_add(c[0], c_rc[96 + r]));
+        const uint32_t s = p2_fp_add(y, T);                    // sum of the whole state after the S-box
         uint32_t rr[23];
         {
             const uint32_t q = __umulhi(y, c_diag_shoup[0]);
             uint32_t t = y * c_diag_plain[0] - q * P;
             t = addmin(t, 0u - P, t);
-            c[0] = fp_add(t, s);
+            c[0] = p2_fp_add(t, s);
         }
 #pragma unroll
         for (int i = 1; i < 24; i++) {
             const uint32_t q = __umulhi(c[i], c_diag_shoup[i]);
             const uint32_t t = c[i] * c_diag_plain[i] - q * P;
             rr[i - 1] = addmin(t, 0u - P, t);                  // canonical
-            c[i] = rr[i - 1] + s;                              // lazy: < 2p < 2^32
+            c[i] = p2_add32(rr[i - 1], s);                     // lazy: < 2p < 2^32
         }
         T = fp_sum64<23>(rr, (uint64_t)s * 23u);               // < 46p
     }
@@ -218,8 +237,8 @@ __device__ __forceinline__ void p2_internal_rounds_hybrid(uint32_t (&c)[24]) {
     }
 #pragma unroll 1
     for (int r = 0; r < 21; r++) {
-        const uint32_t y = p2_sbox(fp_add(c[0], c_rc[96 + r]));
-        const uint32_t s = fp_add(y, T);
+        const uint32_t y = p2_sbox(p2_fp_add(c[0], c_rc[96 + r]));
+        const uint32_t s = p2_fp_add(y, T);
         // X = s << 32 when s < (p+1)/2, else (2s - p) << 31 = {hi: s - (p+1)/2, lo: 2^31}: both are s * 2^32 mod p
         const uint32_t xhi = addmin(s, 0u - HALF, s);
         const uint32_t xlo = (s - xhi) << 31;                  // (p+1)/2 is odd
@@ -235,7 +254,7 @@ __device__ __forceinline__ void p2_internal_rounds_hybrid(uint32_t (&c)[24]) {
                 const uint32_t q = __umulhi(c[i], c_diag_shoup[i]);
                 const uint32_t t = c[i] * c_diag_plain[i] - q * P;
                 o[i - 1] = addmin(t, 0u - P, t);
-                c[i] = o[i - 1] + s;
+                c[i] = p2_add32(o[i - 1], s);
             }
         }
         T = fp_sum64<23>(o, (uint64_t)s * (uint32_t)(24 - (K > 1 ? K : 1)));

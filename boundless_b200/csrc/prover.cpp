@@ -100,6 +100,9 @@ struct Slot {
     cudaStream_t copy_stream = nullptr; cudaEvent_t ev_staged = nullptr;
     const uint32_t* staged_src = nullptr; size_t staged_words = 0;
     b200_circuit last_circuit{}; bool has_seal = false;     // what s.seal holds (for verify of the slot's own proof)
+    // verdicts travel device -> PINNED host words (a D2H copy into pageable memory would block the enqueueing thread until the stream
+    // drains); b200_prover_wait hands them to the caller's ints
+    int* h_vpin = nullptr; int* user_verdict[8] = {}; int n_verdicts = 0;
 };
 
 }  // namespace b200
@@ -262,7 +265,7 @@ static const char* prove_on_slot(b200_prover* p, Slot& s, const b200_circuit& c,
     CU(cudaMemcpyAsync(s.d_trees, s.h_trees.data(), s.h_trees.size() * sizeof(GatherTree), cudaMemcpyHostToDevice, st));
     KL(launch_gather_queries(s.seal, L.off_queries, L.query_words, s.pos, s.d_trees, (uint32_t)s.h_trees.size(), st));
 
-    CU(cudaMemcpyAsync(h_seal, s.seal, (size_t)L.total * 4, cudaMemcpyDeviceToHost, st));
+    if (h_seal) CU(cudaMemcpyAsync(h_seal, s.seal, (size_t)L.total * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(s.ev_end, st));
     s.busy = true; s.h_seal_out = h_seal; s.seal_words = L.total;
     s.last_circuit = c; s.has_seal = true;
@@ -271,7 +274,7 @@ static const char* prove_on_slot(b200_prover* p, Slot& s, const b200_circuit& c,
 
 // verify_integrity of the seal held in s.seal (circuit c): replay the transcript, then check the 50 queries in parallel.
 // Uses the slot's challenge / transcript scratch, so it is ordered after any proof on the same slot by the stream.
-static const char* verify_on_slot(b200_prover* p, Slot& s, const b200_circuit& c, int* h_result) {
+static const char* verify_on_slot(b200_prover* p, Slot& s, const b200_circuit& c, int* h_result, bool check_header = false) {
     cudaStream_t st = s.stream;
     const uint32_t po2 = c.po2, N = 1u << po2, D = 4 * N;
     const uint32_t W = c.w_code + c.w_data + c.w_accum, T = W + c.w_accum + CHECK_COLS;
@@ -290,6 +293,7 @@ static const char* verify_on_slot(b200_prover* p, Slot& s, const b200_circuit& c
     const uint32_t widths[4] = {c.w_code, c.w_data, c.w_accum, (uint32_t)CHECK_COLS};
 
     KL(launch_verify_reset(s.vctx, st));
+    if (check_header) KL(launch_verify_header(s.vctx, seal, c.po2, c.w_code, c.w_data, c.w_accum, c.kind, st));
     KL(launch_verify_canonical(s.vctx, seal, L.total, st));
     KL(launch_iop_init(s.tr, st));
     KL(launch_iop_commit_elems(s.tr, seal, GLOBALS, nullptr, st));
@@ -328,19 +332,26 @@ static const char* verify_on_slot(b200_prover* p, Slot& s, const b200_circuit& c
     KL(launch_iop_draw_bits(s.tr, s.pos, QUERIES, po2 + 2, st));
     KL(launch_verify_queries(s.vctx, seal, sh, s.mp, s.pts, fmix, s.pos, st));
     KL(launch_verify_finish(s.vctx, st));
-    CU(cudaMemcpyAsync(h_result, s.vctx + VCTX_RESULT, 4, cudaMemcpyDeviceToHost, st));
+    if (s.n_verdicts >= 8) { set_error("b200: too many verifications pending on one slot (call b200_prover_wait)"); return last_error(); }
+    CU(cudaMemcpyAsync(&s.h_vpin[s.n_verdicts], s.vctx + VCTX_RESULT, 4, cudaMemcpyDeviceToHost, st));
+    s.user_verdict[s.n_verdicts++] = h_result;
     s.busy = true;
     return nullptr;
 }
 
-// digest of a seal held in host memory -> d_out8 (device): 1024-row column-major view, hash_rows, fold (K4/K5)
-static const char* seal_digest_async(b200_prover* p, Slot& s, const uint32_t* h_seal, size_t words, uint32_t* h_stage,
+// digest of a seal -> d_out8 (device): 1024-row column-major view, hash_rows, fold (K4/K5).  The seal is read from host memory
+// (staged through the slot's pinned buffer) or, with on_device, straight from caller-owned device memory (no host bounce).
+static const char* seal_digest_async(b200_prover* p, Slot& s, const uint32_t* seal, size_t words, bool on_device, uint32_t* h_stage,
                                      uint32_t* d_scratch_matrix, uint32_t* d_scratch_nodes, uint32_t* d_out8) {
     (void)p;
     const uint32_t rows = 1024; const size_t cols = (words + rows - 1) / rows;
-    memcpy(h_stage, h_seal, words * 4);
     CU(cudaMemsetAsync(d_scratch_matrix, 0, cols * rows * 4, s.stream));
-    CU(cudaMemcpyAsync(d_scratch_matrix, h_stage, words * 4, cudaMemcpyHostToDevice, s.stream));
+    if (on_device) {
+        CU(cudaMemcpyAsync(d_scratch_matrix, seal, words * 4, cudaMemcpyDeviceToDevice, s.stream));
+    } else {
+        memcpy(h_stage, seal, words * 4);
+        CU(cudaMemcpyAsync(d_scratch_matrix, h_stage, words * 4, cudaMemcpyHostToDevice, s.stream));
+    }
     KL(launch_poseidon2_rows(d_scratch_nodes + (size_t)rows * 8, d_scratch_matrix, rows, (uint32_t)cols, rows, s.stream));
     KL(launch_poseidon2_fold_tree(d_scratch_nodes, 10, s.stream));
     CU(cudaMemcpyAsync(d_out8, d_scratch_nodes + 8, 32, cudaMemcpyDeviceToDevice, s.stream));
@@ -379,6 +390,9 @@ const char* b200_prover_create(b200_prover** out, int device, const b200_circuit
             set_error("b200: cudaHostAlloc failed"); b200_prover_destroy(p); return last_error();
         }
         s.h_stage_words = stage_words;
+        if (cudaHostAlloc((void**)&s.h_vpin, 8 * sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+            set_error("b200: cudaHostAlloc failed"); b200_prover_destroy(p); return last_error();
+        }
     }
     *out = p;
     return nullptr;
@@ -391,6 +405,7 @@ void b200_prover_destroy(b200_prover* p) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         if (s.arena.base) cudaFree(s.arena.base);
         if (s.h_stage) cudaFreeHost(s.h_stage);
+        if (s.h_vpin) cudaFreeHost(s.h_vpin);
         if (s.alt_alloc) cudaFree(s.alt_alloc);
         if (s.ev_staged) cudaEventDestroy(s.ev_staged);
         if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
@@ -463,19 +478,17 @@ const char* b200_prefetch_trace_async(b200_prover* p, uint32_t slot, const b200_
     return nullptr;
 }
 
-const char* b200_recursion_async(b200_prover* p, uint32_t slot, const b200_circuit* c, const uint32_t* h_a, size_t wa,
-                                 const uint32_t* h_b, size_t wb, uint32_t* h_seal) {
-    const char* e = slot_check(p, slot, c);
-    if (e) return e;
-    if (!h_seal || !h_a || wa == 0) { set_error("b200: null argument"); return last_error(); }
-    Slot& s = p->slots[slot];
+// recursion proof on a slot that has been checked already.  The children are digested BEFORE the new globals are written, so a child
+// may be the slot's own previous seal (lift right behind prove_segment, no copy).
+static const char* recursion_on_slot(b200_prover* p, Slot& s, const b200_circuit* c, const uint32_t* h_a, size_t wa,
+                                     const uint32_t* h_b, size_t wb, bool on_device, uint32_t* h_seal) {
+    const char* e;
     if (wa + wb > s.h_stage_words) { set_error("b200: child seal too large"); return last_error(); }
-    CU(cudaEventRecord(s.ev_begin, s.stream));
-    KL(launch_set_globals(s.seal, c->po2, c->w_code, c->w_data, c->w_accum, c->kind, 0, 0, s.stream));
     // scratch: the evaluation / node regions are free until the proof starts
-    if ((e = seal_digest_async(p, s, h_a, wa, s.h_stage, s.evals, s.nodes[0], s.digests + 8))) return e;
+    if ((e = seal_digest_async(p, s, h_a, wa, on_device, s.h_stage, s.evals, s.nodes[0], s.digests + 8))) return e;
+    if (h_b && wb && (e = seal_digest_async(p, s, h_b, wb, on_device, s.h_stage + wa, s.evals, s.nodes[0], s.digests + 16))) return e;
+    KL(launch_set_globals(s.seal, c->po2, c->w_code, c->w_data, c->w_accum, c->kind, 0, 0, s.stream));
     if (h_b && wb) {
-        if ((e = seal_digest_async(p, s, h_b, wb, s.h_stage + wa, s.evals, s.nodes[0], s.digests + 16))) return e;
         KL(launch_hash_pair_one(s.seal + 8, s.digests + 8, s.digests + 16, s.stream));
     } else {
         CU(cudaMemcpyAsync(s.seal + 8, s.digests + 8, 32, cudaMemcpyDeviceToDevice, s.stream));
@@ -483,6 +496,156 @@ const char* b200_recursion_async(b200_prover* p, uint32_t slot, const b200_circu
     // trace seed = first two words of the input digest
     CU(cudaMemcpyAsync(s.digests, s.seal + 8, 8, cudaMemcpyDeviceToDevice, s.stream));
     return prove_on_slot(p, s, *c, 0, true, nullptr, h_seal);
+}
+static const char* recursion_common(b200_prover* p, uint32_t slot, const b200_circuit* c, const uint32_t* h_a, size_t wa,
+                                    const uint32_t* h_b, size_t wb, bool on_device, uint32_t* h_seal) {
+    const char* e = slot_check(p, slot, c);
+    if (e) return e;
+    if (!h_seal || !h_a || wa == 0) { set_error("b200: null argument"); return last_error(); }
+    Slot& s = p->slots[slot];
+    CU(cudaEventRecord(s.ev_begin, s.stream));
+    return recursion_on_slot(p, s, c, h_a, wa, h_b, wb, on_device, h_seal);
+}
+
+// ---- the agent's task bodies as single enqueues (no host round trip between their steps) ----------------------------------------
+// tasks::prove::prover (prover/crates/workflow/src/tasks/prove.rs:44-108): prove_segment -> verify_integrity -> lift -> verify_integrity.
+// The lift reads the segment seal where the proof left it (the slot's seal buffer).  Outputs, all optional: the segment seal and the
+// lifted seal in pinned host memory, the lifted seal in caller-owned device memory (for the join that follows, local or on a peer GPU),
+// and the two verdicts (0 = valid; NULL skips both verifications).  Everything is valid after b200_prover_wait.
+const char* b200_prove_lift_async(b200_prover* p, uint32_t slot, const b200_circuit* seg, uint64_t seed, const uint32_t* h_trace,
+                                  const b200_circuit* lift, uint32_t* h_seg_seal, uint32_t* h_lift_seal, uint32_t* d_lift_seal,
+                                  int* h_verdicts) {
+    const char* e = slot_check(p, slot, seg);
+    if (e) return e;
+    const char* ce = check_circuit(lift);
+    if (ce) { set_error("%s", ce); return last_error(); }
+    if (lift->po2 > p->maxc.po2 || lift->w_code + lift->w_data + lift->w_accum > p->maxc.w_code + p->maxc.w_data + p->maxc.w_accum ||
+        lift->w_accum > p->maxc.w_accum) { set_error("b200: lift circuit exceeds the prover's max_circuit"); return last_error(); }
+    Slot& s = p->slots[slot];
+    CU(cudaEventRecord(s.ev_begin, s.stream));
+    KL(launch_set_globals(s.seal, seg->po2, seg->w_code, seg->w_data, seg->w_accum, seg->kind, seed, 1, s.stream));
+    bool staged = false;
+    if (h_trace && s.staged_src == h_trace && s.staged_words == ((size_t)(seg->w_code + seg->w_data) << seg->po2)) {
+        CU(cudaStreamWaitEvent(s.stream, s.ev_staged, 0));
+        uint32_t* t = s.coeffs; s.coeffs = s.coeffs_alt; s.coeffs_alt = t;
+        staged = true;
+    }
+    s.staged_src = nullptr; s.staged_words = 0;
+    if ((e = prove_on_slot(p, s, *seg, seed, false, h_trace, h_seg_seal, staged))) return e;
+    if (h_verdicts) { h_verdicts[0] = h_verdicts[1] = -1; if ((e = verify_on_slot(p, s, *seg, &h_verdicts[0], true))) return e; }
+    const size_t seg_words = SealLayout(*seg).total;
+    if ((e = recursion_on_slot(p, s, lift, s.seal, seg_words, nullptr, 0, true, h_lift_seal))) return e;
+    if (h_verdicts && (e = verify_on_slot(p, s, *lift, &h_verdicts[1], true))) return e;
+    if (d_lift_seal) CU(cudaMemcpyAsync(d_lift_seal, s.seal, (size_t)SealLayout(*lift).total * 4, cudaMemcpyDeviceToDevice, s.stream));
+    CU(cudaEventRecord(s.ev_end, s.stream));
+    return nullptr;
+}
+
+// tasks::join::join (tasks/join.rs:41-79; union and resolve have the same shape): verify_integrity of the left and right receipt
+// against the circuits the caller expects them to have, the recursion proof over both, verify_integrity of the result.  The children
+// live in caller-owned DEVICE memory.  h_verdicts[3] = left, right, result (NULL skips the three verifications).
+const char* b200_recursion_verified_async(b200_prover* p, uint32_t slot, const b200_circuit* c, const uint32_t* d_a,
+                                          const b200_circuit* ca, const uint32_t* d_b, const b200_circuit* cb, uint32_t* h_seal,
+                                          uint32_t* d_seal_out, int* h_verdicts) {
+    const char* e = slot_check(p, slot, c);
+    if (e) return e;
+    if (!d_a || !ca || (d_b && !cb)) { set_error("b200: null argument"); return last_error(); }
+    Slot& s = p->slots[slot];
+    const b200_circuit* kids[2] = {ca, d_b ? cb : nullptr};
+    const uint32_t* seals[2] = {d_a, d_b};
+    size_t words[2] = {0, 0};
+    for (int k = 0; k < 2; k++) {
+        if (!kids[k]) continue;
+        const char* ce = check_circuit(kids[k]);
+        if (ce) { set_error("%s", ce); return last_error(); }
+        words[k] = SealLayout(*kids[k]).total;
+        if (words[k] > (size_t)SealLayout(p->maxc).total || kids[k]->po2 > p->maxc.po2) { set_error("b200: child circuit exceeds the prover's max_circuit"); return last_error(); }
+    }
+    CU(cudaEventRecord(s.ev_begin, s.stream));
+    if (h_verdicts) {
+        h_verdicts[0] = h_verdicts[2] = -1; h_verdicts[1] = d_b ? -1 : 0;
+        for (int k = 0; k < 2; k++) {
+            if (!kids[k]) continue;
+            CU(cudaMemcpyAsync(s.seal, seals[k], words[k] * 4, cudaMemcpyDeviceToDevice, s.stream));
+            if ((e = verify_on_slot(p, s, *kids[k], &h_verdicts[k], true))) return e;
+        }
+    }
+    if ((e = recursion_on_slot(p, s, c, d_a, words[0], d_b, words[1], true, h_seal))) return e;
+    if (h_verdicts && (e = verify_on_slot(p, s, *c, &h_verdicts[2], true))) return e;
+    if (d_seal_out) CU(cudaMemcpyAsync(d_seal_out, s.seal, (size_t)SealLayout(*c).total * 4, cudaMemcpyDeviceToDevice, s.stream));
+    CU(cudaEventRecord(s.ev_end, s.stream));
+    return nullptr;
+}
+
+const char* b200_recursion_async(b200_prover* p, uint32_t slot, const b200_circuit* c, const uint32_t* h_a, size_t wa,
+                                 const uint32_t* h_b, size_t wb, uint32_t* h_seal) {
+    return recursion_common(p, slot, c, h_a, wa, h_b, wb, false, h_seal);
+}
+// The same with the child seals in DEVICE memory (receipts that stay on the GPU between prove, lift and join, or arrive from a peer
+// GPU over NVLink): no host staging.  The buffers are read on the slot's stream; the caller keeps them valid until b200_prover_wait.
+const char* b200_recursion_dev_async(b200_prover* p, uint32_t slot, const b200_circuit* c, const uint32_t* d_a, size_t wa,
+                                     const uint32_t* d_b, size_t wb, uint32_t* h_seal) {
+    return recursion_common(p, slot, c, d_a, wa, d_b, wb, true, h_seal);
+}
+
+// Copy the seal the slot produced last (or is producing: the copy is ordered behind it on the slot's stream) into caller-owned device
+// memory, so that a receipt can be handed to the next recursion step or to NCCL without leaving the GPU.
+const char* b200_seal_to_device(b200_prover* p, uint32_t slot, uint32_t* d_dst, size_t words) {
+    if (!p || slot >= p->slots.size()) { set_error("b200: bad prover/slot"); return last_error(); }
+    Slot& s = p->slots[slot];
+    if (!d_dst) { set_error("b200: null d_dst"); return last_error(); }
+    if (!s.has_seal || words != (size_t)SealLayout(s.last_circuit).total) { set_error("b200: slot %u holds no seal of %zu words", slot, words); return last_error(); }
+    CU(cudaSetDevice(p->device));
+    CU(cudaMemcpyAsync(d_dst, s.seal, words * 4, cudaMemcpyDeviceToDevice, s.stream));
+    return nullptr;
+}
+
+// 1 when everything enqueued on the slot has completed, 0 while it is still running, -1 on error (b200_last_error).  Never blocks:
+// lets one host thread keep several slots and NCCL transfers in flight and react to whichever finishes first.
+int b200_prover_query(b200_prover* p, uint32_t slot) {
+    if (!p || slot >= p->slots.size()) { set_error("b200: bad prover/slot"); return -1; }
+    if (cudaSetDevice(p->device) != cudaSuccess) { set_error("b200: cudaSetDevice failed"); return -1; }
+    cudaError_t e = cudaStreamQuery(p->slots[slot].stream);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) return 0;
+    set_error("b200: cudaStreamQuery: %s", cudaGetErrorString(e));
+    return -1;
+}
+
+// verify_integrity against the circuit the CALLER expects (shape and kind): a seal whose header says anything else is rejected with
+// code 103 instead of being verified as whatever it claims to be.  seal == NULL: the seal the slot produced last; otherwise `words`
+// words in host memory (seal_on_device == 0) or caller-owned device memory (!= 0, read on the slot's stream).
+const char* b200_verify_circuit_async(b200_prover* p, uint32_t slot, const b200_circuit* expect, const uint32_t* seal, size_t words,
+                                      int seal_on_device, int* h_result) {
+    if (!p || slot >= p->slots.size()) { set_error("b200: bad prover/slot"); return last_error(); }
+    if (!h_result) { set_error("b200: null h_result"); return last_error(); }
+    const char* ce = check_circuit(expect);
+    if (ce) { set_error("%s", ce); return last_error(); }
+    Slot& s = p->slots[slot];
+    const b200_circuit c = *expect;
+    if (c.po2 > p->maxc.po2 || c.w_code + c.w_data + c.w_accum > p->maxc.w_code + p->maxc.w_data + p->maxc.w_accum ||
+        c.w_accum > p->maxc.w_accum || SealLayout(c).total > SealLayout(p->maxc).total) {
+        set_error("b200: expected circuit exceeds the prover's max_circuit"); return last_error();
+    }
+    CU(cudaSetDevice(p->device));
+    if (seal) {
+        if (s.busy) { set_error("b200: slot %u busy (call b200_prover_wait first)", slot); return last_error(); }
+        if ((size_t)SealLayout(c).total != words) { *h_result = 102; return nullptr; }
+        if (seal_on_device) {
+            CU(cudaMemcpyAsync(s.seal, seal, words * 4, cudaMemcpyDeviceToDevice, s.stream));
+        } else {
+            if (words > s.h_stage_words) { set_error("b200: seal too large for the staging buffer"); return last_error(); }
+            memcpy(s.h_stage, seal, words * 4);
+            CU(cudaMemcpyAsync(s.seal, s.h_stage, words * 4, cudaMemcpyHostToDevice, s.stream));
+        }
+        s.last_circuit = c; s.has_seal = true;
+    } else if (!s.has_seal) {
+        set_error("b200: slot %u holds no seal to verify", slot); return last_error();
+    } else if ((size_t)SealLayout(c).total != (size_t)SealLayout(s.last_circuit).total) {
+        *h_result = 102; return nullptr;
+    }
+    *h_result = -1;
+    return verify_on_slot(p, s, c, h_result, true);
 }
 
 // verify_integrity: h_seal == NULL verifies the seal the slot produced last (still resident on the device)
@@ -520,8 +683,10 @@ const char* b200_prover_wait(b200_prover* p, uint32_t slot) {
     if (!p || slot >= p->slots.size()) { set_error("b200: bad prover/slot"); return last_error(); }
     Slot& s = p->slots[slot];
     s.busy = false;                       // whatever happens below, the slot is reusable afterwards
+    const int nv = s.n_verdicts; s.n_verdicts = 0;
     CU(cudaSetDevice(p->device));
     CU(cudaStreamSynchronize(s.stream));
+    for (int i = 0; i < nv; i++) if (s.user_verdict[i]) *s.user_verdict[i] = s.h_vpin[i];
     return nullptr;
 }
 

@@ -71,6 +71,13 @@ __global__ void k_verify_canonical(uint32_t* __restrict__ ctx, const uint32_t* _
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) bad |= seal[i] >= P;
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicMax(&ctx[VCTX_RC], 106u);
 }
+// ---- (0) the header must name the circuit the caller expects (shape AND kind); the spare header words must be zero ----------------
+__global__ void k_verify_header(uint32_t* __restrict__ ctx, const uint32_t* __restrict__ seal, uint32_t po2, uint32_t w_code,
+                                uint32_t w_data, uint32_t w_accum, uint32_t kind) {
+    const bool ok = seal[0] == po2 && seal[1] == w_code && seal[2] == w_data && seal[3] == w_accum && seal[4] == kind &&
+                    seal[5] == 0 && seal[6] == 0 && seal[7] == 0;
+    if (!ok) atomicMax(&ctx[VCTX_RC], 103u);
+}
 __global__ void k_verify_reset(uint32_t* ctx) {
     for (uint32_t i = threadIdx.x; i < VCTX_WORDS; i += blockDim.x) ctx[i] = 0;
 }
@@ -302,6 +309,10 @@ __global__ void k_verify_finish(uint32_t* __restrict__ ctx) {
 }
 
 cudaError_t launch_verify_reset(uint32_t* ctx, cudaStream_t s) { B200_LAUNCH(k_verify_reset)<<<1, 128, 0, s>>>(ctx); return cudaGetLastError(); }
+cudaError_t launch_verify_header(uint32_t* ctx, const uint32_t* seal, uint32_t po2, uint32_t w_code, uint32_t w_data, uint32_t w_accum,
+                                 uint32_t kind, cudaStream_t s) {
+    B200_LAUNCH(k_verify_header)<<<1, 1, 0, s>>>(ctx, seal, po2, w_code, w_data, w_accum, kind); return cudaGetLastError();
+}
 cudaError_t launch_verify_canonical(uint32_t* ctx, const uint32_t* seal, uint32_t words, cudaStream_t s) {
     uint32_t grid = (words + 255) / 256; if (grid > 148) grid = 148;
     B200_LAUNCH(k_verify_canonical)<<<grid, 256, 0, s>>>(ctx, seal, words); return cudaGetLastError();

@@ -67,7 +67,14 @@ SYMBOLS = {
     "b200_prove_segment_async": (_cp, [_vp, _u32, C.POINTER(Circuit), _u64, _vp, _vp]),
     "b200_prefetch_trace_async": (_cp, [_vp, _u32, C.POINTER(Circuit), _vp]),
     "b200_recursion_async": (_cp, [_vp, _u32, C.POINTER(Circuit), _vp, _sz, _vp, _sz, _vp]),
+    "b200_recursion_dev_async": (_cp, [_vp, _u32, C.POINTER(Circuit), _vp, _sz, _vp, _sz, _vp]),
+    "b200_prove_lift_async": (_cp, [_vp, _u32, C.POINTER(Circuit), _u64, _vp, C.POINTER(Circuit), _vp, _vp, _vp, C.POINTER(C.c_int)]),
+    "b200_recursion_verified_async": (_cp, [_vp, _u32, C.POINTER(Circuit), _vp, C.POINTER(Circuit), _vp, C.POINTER(Circuit), _vp, _vp,
+                                            C.POINTER(C.c_int)]),
+    "b200_seal_to_device": (_cp, [_vp, _u32, _vp, _sz]),
+    "b200_prover_query": (C.c_int, [_vp, _u32]),
     "b200_verify_async": (_cp, [_vp, _u32, _vp, _sz, C.POINTER(C.c_int)]),
+    "b200_verify_circuit_async": (_cp, [_vp, _u32, C.POINTER(Circuit), _vp, _sz, C.c_int, C.POINTER(C.c_int)]),
     "b200_prover_wait": (_cp, [_vp, _u32]),
     "b200_prover_last_ms": (C.c_float, [_vp, _u32]),
     "b200_prover_mark": (_cp, [_vp, _u32, _u32]),

@@ -82,9 +82,23 @@ class VerifierContext:
 class VerificationError(B200Error):
     """`verify_integrity` failed: the reference's `Err` from `verify_integrity_with_context` (tasks/prove.rs:56-58)."""
 
-    def __init__(self, code):
-        super().__init__("seal does not verify (check %d failed)" % code)
+    def __init__(self, code, what=""):
+        super().__init__("%sseal does not verify (check %d failed)" % (what + ": " if what else "", code))
         self.code = code
+        self.what = what
+
+
+@dataclass
+class DeviceReceipt:
+    """A succinct receipt whose seal lives in DEVICE memory (caller-owned buffer of `words` u32 at `ptr`): what moves between prove, lift
+    and join on one GPU, or over NVLink between GPUs, without a host bounce.  `owner` keeps the backing allocation alive."""
+    ptr: int
+    words: int
+    kind: int
+    claim: tuple = field(default_factory=tuple)
+    assumptions: list = field(default_factory=list)
+    owner: object = None
+    seal: Optional[np.ndarray] = None          # host copy, when one was asked for
 
 
 class _Pinned:
@@ -116,6 +130,8 @@ class ProverServer:
         self.h = h
         max_words = max(self.seal_words(self.seg_circuit), self.seal_words(self._rec_circuit(KIND_LIFT)))
         self._seal_bufs = [_Pinned(self.L, max_words) for _ in range(opts.slots)]
+        self._seal_bufs2 = [_Pinned(self.L, max_words) for _ in range(opts.slots)]      # second output of the composite tasks
+        self._verdicts3 = [(C.c_int * 3)() for _ in range(opts.slots)]
         self._pending = [None] * opts.slots
         self._prefetched = [None] * opts.slots
         self._verdict = [C.c_int(0) for _ in range(opts.slots)]
@@ -142,7 +158,7 @@ class ProverServer:
                     self.L.b200_prover_wait(self.h, s)
             self.L.b200_prover_destroy(self.h)
             self.h = None
-            for b in self._seal_bufs:
+            for b in self._seal_bufs + self._seal_bufs2:
                 b.free()
 
     def __del__(self):
@@ -208,15 +224,106 @@ class ProverServer:
         asm = list(a.assumptions) + (list(b.assumptions) if b is not None and kind == KIND_JOIN else [])
         return SuccinctReceipt(seal, kind, (lo, hi), asm if kind != KIND_UNION else [])
 
+    # -- the agent's task bodies as single enqueues (device-resident receipts) ---------------------------------------------------
+    def submit_prove_lift(self, slot, segment: Segment, d_out: int = 0, verify: bool = True, host_seals: bool = True):
+        """tasks::prove::prover (tasks/prove.rs:44-108) as ONE enqueue: prove_segment -> verify_integrity -> lift -> verify_integrity, no host
+        round trip in between.  `d_out` (optional): device buffer that receives the lifted seal.  wait_task(slot) returns the receipts."""
+        c = Circuit(segment.po2, *self.opts.segment_widths, KIND_SEGMENT)
+        lc = self._rec_circuit(KIND_LIFT)
+        tr = None
+        if segment.trace is not None:
+            tr = np.ascontiguousarray(segment.trace, dtype=np.uint32)
+            if tr.size != (c.w_code + c.w_data) << c.po2:
+                raise B200Error("segment trace has %d words, expected %d" % (tr.size, (c.w_code + c.w_data) << c.po2))
+        v = self._verdicts3[slot] if 0 <= slot < len(self._verdicts3) else self._verdicts3[0]
+        _lib.check(self.L.b200_prove_lift_async(
+            self.h, slot, C.byref(c), segment.seed, tr.ctypes.data_as(C.c_void_p) if tr is not None else None, C.byref(lc),
+            self._buf(slot) if host_seals else None, self._seal_bufs2[slot].ptr if host_seals and 0 <= slot < len(self._seal_bufs2) else None,
+            C.c_void_p(d_out) if d_out else None, C.cast(v, C.POINTER(C.c_int)) if verify else None))
+        self._pending[slot] = ("prove_lift", (c, lc), (segment, d_out, verify, host_seals), tr)
+
+    def submit_recursion_dev(self, slot, kind, a: "DeviceReceipt", b: Optional["DeviceReceipt"] = None, d_out: int = 0,
+                             verify: bool = True, host_seal: bool = True):
+        """tasks::join::join (tasks/join.rs:41-79; union / resolve alike) as ONE enqueue over device-resident receipts: verify_integrity of
+        left and right against the circuits their metadata names, the recursion proof, verify_integrity of the result."""
+        c = self._rec_circuit(kind)
+        ca = self._rec_circuit(a.kind)
+        cb = self._rec_circuit(b.kind) if b is not None else None
+        v = self._verdicts3[slot] if 0 <= slot < len(self._verdicts3) else self._verdicts3[0]
+        _lib.check(self.L.b200_recursion_verified_async(
+            self.h, slot, C.byref(c), C.c_void_p(a.ptr), C.byref(ca), C.c_void_p(b.ptr) if b is not None else None,
+            C.byref(cb) if cb is not None else None, self._buf(slot) if host_seal else None, C.c_void_p(d_out) if d_out else None,
+            C.cast(v, C.POINTER(C.c_int)) if verify else None))
+        self._pending[slot] = ("recursion_dev", c, (kind, a, b, d_out, verify, host_seal), None)
+
+    def query(self, slot) -> bool:
+        """True once everything enqueued on the slot has completed (never blocks); wait()/wait_task() then returns at once."""
+        r = self.L.b200_prover_query(self.h, slot)
+        if r < 0:
+            _lib.check(self.L.b200_last_error())
+        return r == 1
+
+    def wait_task(self, slot):
+        """Completion of submit_prove_lift -> (SegmentReceipt | None, DeviceReceipt) or submit_recursion_dev -> DeviceReceipt.  Raises
+        VerificationError naming the step whose verify_integrity failed (the agent turns that into a task retry / failure)."""
+        pend = self._pending[slot]
+        if pend is None or pend[0] not in ("prove_lift", "recursion_dev"):
+            raise B200Error("slot %d has no composite task in flight" % slot)
+        _lib.check(self.L.b200_prover_wait(self.h, slot))
+        self._pending[slot] = None
+        v = self._verdicts3[slot]
+        if pend[0] == "prove_lift":
+            (c, lc), (segment, d_out, verify, host_seals) = pend[1], pend[2]
+            if verify:
+                for code, what in ((v[0], "segment receipt"), (v[1], "lift receipt")):
+                    if code != 0:
+                        raise VerificationError(int(code), what)
+            seg_r = lift_seal = None
+            if host_seals:
+                seg_r = SegmentReceipt(self._seal_bufs[slot].array[: self.seal_words(c)].copy(), segment.index, segment.po2,
+                                       list(segment.assumptions))
+                lift_seal = self._seal_bufs2[slot].array[: self.seal_words(lc)].copy()
+            return seg_r, DeviceReceipt(d_out, self.seal_words(lc), KIND_LIFT, (segment.index, segment.index), list(segment.assumptions),
+                                        None, lift_seal)
+        c, (kind, a, b, d_out, verify, host_seal) = pend[1], pend[2]
+        if verify:
+            for code, what in ((v[0], "left receipt"), (v[1], "right receipt"), (v[2], "joined receipt")):
+                if code != 0:
+                    raise VerificationError(int(code), what)
+        seal = self._seal_bufs[slot].array[: self.seal_words(c)].copy() if host_seal else None
+        if kind == KIND_RESOLVE:
+            gone = b.claim_digest() if hasattr(b, "claim_digest") else None
+            return DeviceReceipt(d_out, self.seal_words(c), kind, tuple(a.claim), [x for x in a.assumptions if x != gone], None, seal)
+        last = b if b is not None else a
+        asm = list(a.assumptions) + (list(b.assumptions) if b is not None and kind == KIND_JOIN else [])
+        return DeviceReceipt(d_out, self.seal_words(c), kind, (a.claim[0], last.claim[1]), asm if kind != KIND_UNION else [], None, seal)
+
     # -- verify_integrity on the device (tasks/prove.rs:56-58, :106-108; tasks/join.rs:77-79) ---------------------------
-    def submit_verify(self, slot, receipt=None):
+    def expected_circuit(self, receipt):
+        """The circuit a receipt of this type MUST have been proved with on this server: segment receipts carry their po2 (bounded by
+        the provisioned one), succinct receipts are recursion-shaped with the kind their metadata names.  verify_integrity checks the
+        seal's header against it, so a small seal of another kind cannot pass as a lift or join receipt."""
+        if isinstance(receipt, SegmentReceipt):
+            return Circuit(receipt.po2, *self.opts.segment_widths, KIND_SEGMENT)
+        return self._rec_circuit(receipt.kind)
+
+    def submit_verify(self, slot, receipt=None, expect: Optional[Circuit] = None):
         """Enqueue the verification of `receipt` (slot must be idle) or, with receipt=None, of the seal the slot is producing
         (may follow submit_segment / submit_recursion directly: same stream, no host round trip).  wait_verify() gives the verdict."""
         if receipt is None:
-            _lib.check(self.L.b200_verify_async(self.h, slot, None, 0, C.byref(self._verdict[slot])))
+            if expect is None:
+                _lib.check(self.L.b200_verify_async(self.h, slot, None, 0, C.byref(self._verdict[slot])))
+            else:
+                _lib.check(self.L.b200_verify_circuit_async(self.h, slot, C.byref(expect), None, 0, 0, C.byref(self._verdict[slot])))
             return None
+        c = expect or self.expected_circuit(receipt)
+        if isinstance(receipt, DeviceReceipt) and receipt.seal is None:
+            _lib.check(self.L.b200_verify_circuit_async(self.h, slot, C.byref(c), C.c_void_p(receipt.ptr), receipt.words, 1,
+                                                        C.byref(self._verdict[slot])))
+            return receipt
         seal = np.ascontiguousarray(receipt.seal, dtype=np.uint32)
-        _lib.check(self.L.b200_verify_async(self.h, slot, seal.ctypes.data_as(C.c_void_p), seal.size, C.byref(self._verdict[slot])))
+        _lib.check(self.L.b200_verify_circuit_async(self.h, slot, C.byref(c), seal.ctypes.data_as(C.c_void_p), seal.size, 0,
+                                                    C.byref(self._verdict[slot])))
         return seal
 
     def wait_verify(self, slot):
@@ -232,6 +339,15 @@ class ProverServer:
         keep = self.submit_verify(slot, receipt)
         self.wait_verify(slot)
         del keep
+
+    def verify_seal(self, seal, slot=0):
+        """Header-trusting form (b200_verify_async): checks the seal as a proof of whatever circuit its own header names.  For tooling and
+        the verifier-parity tests; the agent path uses verify_integrity, which binds the circuit the receipt is SUPPOSED to have."""
+        if self._pending[slot] is not None:
+            raise B200Error("slot %d busy" % slot)
+        seal = np.ascontiguousarray(seal, dtype=np.uint32)
+        _lib.check(self.L.b200_verify_async(self.h, slot, seal.ctypes.data_as(C.c_void_p), seal.size, C.byref(self._verdict[slot])))
+        self.wait_verify(slot)
 
     def last_ms(self, slot):
         return float(self.L.b200_prover_last_ms(self.h, slot))

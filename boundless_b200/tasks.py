@@ -87,6 +87,10 @@ class AgentArgs:
     resolve_timeout: int = 10
     finalize_retries: int = 0
     finalize_timeout: int = 10
+    # executor.rs:517-545: with JOIN_STREAM / UNION_STREAM set in the environment, join (and resolve) / union tasks go to the customer's
+    # "join" stream instead of the prove stream, so dedicated workers can take them.  None = read the environment like the reference.
+    join_stream: Optional[bool] = None
+    union_stream: Optional[bool] = None
 
 
 class Agent:
@@ -220,8 +224,11 @@ def finalize(agent: Agent, job_id: str) -> List[str]:
     # rollup_receipt.verify(image_id): the succinct receipt must verify and must have no unresolved assumptions
     if root.assumptions:
         raise TaskError("[BENTO-FINALIZE-001] Receipt verification failed", "unresolved assumptions")
-    if agent.prover is not None:
-        agent._verify(root, "[BENTO-FINALIZE-001] Receipt verification failed")
+    # never skipped: a worker without a verifier must not upload a receipt nobody checked (the reference's finalize always verifies,
+    # tasks/finalize.rs:69).  What is NOT bound on the synthetic path: image_id and the claim -- the real binding is the recursion
+    # circuit's own constraint system (out of scope), see DESIGN.md "known gaps".
+    agent._prover("[BENTO-FINALIZE-001] Receipt verification failed: this worker has no verifier")
+    agent._verify(root, "[BENTO-FINALIZE-001] Receipt verification failed")
     key = "%s/%s/%s.bincode" % (wire.RECEIPT_BUCKET_DIR, wire.STARK_BUCKET_DIR, job_id)
     _ctx("Failed to upload final receipt to shared storage", agent.store.write_asset, key, wire.serialize_rollup(root, journal))
     return [root_key, journal_key, image_key]
@@ -287,7 +294,18 @@ def executor(agent: Agent, job_id: str, request: wire.ExecutorReq) -> ExecutorRe
         raise TaskError("Customer %s missing aux stream" % request.user_id)
     if prove_stream is None:
         raise TaskError("Customer %s missing gpu prove stream" % request.user_id)
-    streams = {"prove": prove_stream, "join": prove_stream, "union": prove_stream, "aux": aux_stream}   # JOIN_STREAM etc. unset
+    import os
+    a = agent.args
+    join_stream = union_stream = prove_stream
+    if a.join_stream if a.join_stream is not None else "JOIN_STREAM" in os.environ:
+        join_stream = db.get_stream(request.user_id, wire.JOIN_WORK_TYPE)
+        if join_stream is None:
+            raise TaskError("Customer %s missing gpu join stream" % request.user_id)
+    if a.union_stream if a.union_stream is not None else "UNION_STREAM" in os.environ:
+        union_stream = db.get_stream(request.user_id, wire.JOIN_WORK_TYPE)
+        if union_stream is None:
+            raise TaskError("Customer %s missing gpu union stream" % request.user_id)
+    streams = {"prove": prove_stream, "join": join_stream, "union": union_stream, "aux": aux_stream}
     job_prefix = "job:%s" % job_id
     planner = Planner()
     for i in range(n):
@@ -379,4 +397,98 @@ def poll_work(agent: Agent, max_tasks: Optional[int] = None) -> int:
             db.update_task_retry(task.job_id, task.task_id)
         else:
             db.update_task_failed(task.job_id, task.task_id, err_str[:1024])
+    return claimed
+
+
+# ---- the same loop with several Prove claims in flight on one GPU ------------------------------------------------------------------
+def _fail_or_retry(agent: Agent, task: ReadyTask, err_str: str) -> None:
+    """lib.rs:639-677 (shared by poll_work_pipelined): retry while the budget lasts, else fail the task and with it the job."""
+    db = agent.task_db
+    agent.errors.append("%s|%s: %s" % (task.job_id, task.task_id, err_str))
+    if task.max_retries > 0:
+        current = db.get_task_retries_running(task.job_id, task.task_id)
+        if current is not None and current + 1 > task.max_retries:
+            err_str = err_str[:1024]
+            db.update_task_failed(task.job_id, task.task_id, "retry max hit" if not err_str else "retry max hit: %s" % err_str)
+            return
+        db.update_task_retry(task.job_id, task.task_id)
+    else:
+        db.update_task_failed(task.job_id, task.task_id, err_str[:1024])
+
+
+def poll_work_pipelined(agent: Agent, max_tasks: Optional[int] = None) -> int:
+    """Agent::poll_work for a GPU worker whose prover has several proof slots: up to `slots` Prove tasks are claimed and in flight at
+    once, each one the whole body of tasks::prove::prover (prove_segment -> verify_integrity -> lift -> verify_integrity, one enqueue:
+    ProverServer.submit_prove_lift), and a task is marked done only after its lifted receipt is in the hot store -- the reference's
+    ordering (tasks/prove.rs:113-117, lib.rs:781-797).  The reference reaches the same concurrency by running several agent processes;
+    one process per GPU with several slots avoids re-loading tables and contexts.  Any other task type is processed by the plain
+    synchronous path once the proofs in flight have drained.  Returns the number of tasks claimed."""
+    p = agent._prover("[BENTO-PROVE-002] Missing prover from prove task")
+    db = agent.task_db
+    free = list(range(p.opts.slots))
+    inflight = {}                          # slot -> (task, segment_key, output_key)
+    claimed = 0
+
+    def finish(slot):
+        task, segment_key, output_key = inflight.pop(slot)
+        free.append(slot)
+        try:
+            try:
+                _seg, lift = p.wait_task(slot)
+            except Exception as e:        # noqa: BLE001
+                what = getattr(e, "what", "")
+                tag = ("[BENTO-PROVE-004] Failed to verify segment receipt integrity" if what == "segment receipt" else
+                       "[BENTO-PROVE-010] Failed to verify lift receipt integrity" if what == "lift receipt" else "[BENTO-PROVE-003] prove failed")
+                raise TaskError("[BENTO-WF-115] Prove failed", TaskError(tag, e))
+            receipt = SuccinctReceipt(lift.seal, lift.kind, tuple(lift.claim), list(lift.assumptions))
+            blob = _ctx("Failed to serialize the segment", wire.serialize_succinct, receipt)
+            _ctx("Failed to set receipt key with expiry", agent.hot_set_bytes, output_key, blob)
+        except Exception as err:          # noqa: BLE001
+            _fail_or_retry(agent, task, str(err))
+            return
+        db.update_task_done(task.job_id, task.task_id, None)
+        try:
+            agent.hot_delete(segment_key)
+        except Exception:                 # noqa: BLE001
+            pass
+        agent.processed.append("%s|%s" % (task.job_id, task.task_id))
+
+    while True:
+        task = None
+        if free and (max_tasks is None or claimed < max_tasks):
+            task = db.request_work(agent.args.task_stream)
+        if task is None:
+            if not inflight:
+                break
+            done = [s for s in inflight if p.query(s)]
+            for s in done or [next(iter(inflight))]:      # nothing finished yet: block on the oldest
+                finish(s)
+            continue
+        claimed += 1
+        try:
+            task_type = wire.task_type_from_value(task.task_def)
+        except wire.WireError as e:
+            _fail_or_retry(agent, task, str(TaskError("Invalid task_def: %s:%s" % (task.job_id, task.task_id), e)))
+            continue
+        if not isinstance(task_type, wire.ProveReq) or agent.is_povw_enabled():
+            for s in list(inflight):
+                finish(s)
+            try:
+                process_work(agent, task)
+            except Exception as err:      # noqa: BLE001
+                _fail_or_retry(agent, task, str(err))
+            continue
+        try:
+            segment_key = "job:%s:%s:%d" % (task.job_id, wire.SEGMENTS_PATH, task_type.index)
+            segment_vec = _ctx("segment data not found for segment key: %s" % segment_key, agent.hot_get_bytes, segment_key)
+            segment = _ctx("Failed to deserialize segment data from redis", wire.deserialize_segment, segment_vec)
+            slot = free.pop(0)
+            try:
+                p.submit_prove_lift(slot, segment)
+            except Exception:
+                free.insert(0, slot)
+                raise
+            inflight[slot] = (task, segment_key, "job:%s:%s:%s" % (task.job_id, wire.RECUR_RECEIPT_PATH, task.task_id))
+        except Exception as err:          # noqa: BLE001
+            _fail_or_retry(agent, task, str(TaskError("[BENTO-WF-115] Prove failed", err)))
     return claimed

@@ -132,6 +132,27 @@ const char* b200_prefetch_trace_async(b200_prover* p, uint32_t slot, const b200_
 /* lift / join / resolve / union: recursion-shaped proof (kind 1..4) over the digest(s) of the child seal(s) */
 const char* b200_recursion_async(b200_prover* p, uint32_t slot, const b200_circuit* c, const uint32_t* h_seal_a,
                                  size_t words_a, const uint32_t* h_seal_b, size_t words_b, uint32_t* h_seal);
+/* The same with the child seals in DEVICE memory (receipts kept on the GPU between prove, lift and join, or received from a peer
+ * GPU over NVLink): no host staging.  Read on the slot's stream; the caller keeps the buffers valid until b200_prover_wait. */
+const char* b200_recursion_dev_async(b200_prover* p, uint32_t slot, const b200_circuit* c, const uint32_t* d_seal_a,
+                                     size_t words_a, const uint32_t* d_seal_b, size_t words_b, uint32_t* h_seal);
+/* The agent's task bodies as SINGLE enqueues, no host round trip between their steps:
+ * b200_prove_lift_async = tasks::prove::prover (prover/crates/workflow/src/tasks/prove.rs:44-108): prove_segment -> verify_integrity ->
+ *   lift -> verify_integrity.  Optional outputs (NULL = skip): segment / lifted seal in pinned host memory, lifted seal in caller-owned
+ *   device memory, verdicts[2] (0 = valid; NULL skips both verifications).
+ * b200_recursion_verified_async = tasks::join::join (tasks/join.rs:41-79; union / resolve alike): verify_integrity of the left and right
+ *   receipts (DEVICE memory) against the circuits the caller expects, the recursion proof, verify_integrity of the result; verdicts[3].
+ * All outputs are valid after b200_prover_wait(p, slot). */
+const char* b200_prove_lift_async(b200_prover* p, uint32_t slot, const b200_circuit* seg, uint64_t seed, const uint32_t* h_trace,
+                                  const b200_circuit* lift, uint32_t* h_seg_seal, uint32_t* h_lift_seal, uint32_t* d_lift_seal,
+                                  int* h_verdicts);
+const char* b200_recursion_verified_async(b200_prover* p, uint32_t slot, const b200_circuit* c, const uint32_t* d_seal_a,
+                                          const b200_circuit* circuit_a, const uint32_t* d_seal_b, const b200_circuit* circuit_b,
+                                          uint32_t* h_seal, uint32_t* d_seal_out, int* h_verdicts);
+/* D2D copy of the seal the slot produced last (ordered behind the proof on the slot's stream) into caller-owned device memory */
+const char* b200_seal_to_device(b200_prover* p, uint32_t slot, uint32_t* d_dst, size_t words);
+/* 1 = everything enqueued on the slot has completed, 0 = still running, -1 = error.  Never blocks. */
+int b200_prover_query(b200_prover* p, uint32_t slot);
 /* verify_integrity (the check the reference runs after every prove / lift / join: tasks/prove.rs:56-58, tasks/join.rs:77-79),
  * on the device: transcript replay + the 50 queries in parallel.  h_seal == NULL verifies the seal the slot produced last
  * (still resident; may be enqueued right behind b200_prove_segment_async on a busy slot), otherwise `words` words from host
@@ -139,6 +160,11 @@ const char* b200_recursion_async(b200_prover* p, uint32_t slot, const b200_circu
  * (100-102 malformed header/length, 106 non-canonical word, 110 constraint identity, 120+g Merkle path of group g,
  * 130+k / 140+k FRI round k path / value, 150 final polynomial). */
 const char* b200_verify_async(b200_prover* p, uint32_t slot, const uint32_t* h_seal, size_t words, int* h_result);
+/* verify_integrity against the circuit the CALLER expects: the seal's header must equal `expect` (po2, widths, kind), else code 103 --
+ * b200_verify_async above trusts the header, so a small seal of another kind would pass as whatever it says it is.  `seal` NULL = the
+ * slot's own last seal; else `words` words in host memory (seal_on_device == 0) or caller-owned device memory (!= 0). */
+const char* b200_verify_circuit_async(b200_prover* p, uint32_t slot, const b200_circuit* expect, const uint32_t* seal, size_t words,
+                                      int seal_on_device, int* h_result);
 const char* b200_prover_wait(b200_prover* p, uint32_t slot);
 /* device time (ms) between the first and last operation of the slot's last proof */
 float b200_prover_last_ms(b200_prover* p, uint32_t slot);

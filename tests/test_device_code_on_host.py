@@ -40,7 +40,8 @@ def test_poseidon2_kat_from_the_device_source(harness):
                                      ("B200_P2_LAZY=1",), ("B200_P2_LAZY=2",), ("B200_P2_LAZY=4",), ("B200_P2_LAZY=7",), ("B200_P2_LAZY=3",),
                                      ("B200_REDC_V=3",), ("B200_REDC_V=3", "B200_P2_LAZY=7"), ("B200_P2_NMACC=1",), ("B200_P2_NMACC=2", "B200_P2_LAZY=1"),
                                      ("B200_P2_NMACC=8", "B200_P2_LAZY=1"), ("B200_P2_NMACC=23",), ("B200_P2_NMACC=24", "B200_P2_LAZY=1"),
-                                     ("B200_P2_LAZY=3", "B200_P2_SHOUP=0")])
+                                     ("B200_P2_LAZY=3", "B200_P2_SHOUP=0"), ("B200_P2_LAZY=0", "B200_P2_ZALL=0"), ("B200_P2_LAZY=0",), ("B200_P2_ZALL=0",),
+                                     ("B200_P2_LAZY=1", "B200_P2_NMACC=6", "B200_P2_ZALL=1")])
 def test_every_build_variant_passes_the_kat(tmp_path, harness, defines):
     """the measured-and-rejected formulations and the prepared lazy-reduction variants kept behind macros stay
     correct: the KAT, and 3 x 2002 chained permutations of random / all-zero / all-(p-1) states against the default build"""

@@ -243,3 +243,120 @@ def test_po2_21_segment_verifies(gpu, oracle):
         assert oracle.verify(r.seal) == 0
     finally:
         srv.close()
+
+
+# ---- the agent's task bodies as single enqueues over device-resident receipts (round 2) -----------------------------------------------
+def _dev_buf(torch, words):
+    return torch.zeros(words, dtype=torch.int32, device="cuda")
+
+
+def test_prove_lift_composite_is_bit_exact(gpu, small_server, oracle):
+    """b200_prove_lift_async = tasks::prove::prover (prove.rs:44-108) in one enqueue: both seals equal the oracle's, both verdicts are 0,
+    and the lifted seal also lands in the caller's device buffer."""
+    from boundless_b200 import Segment
+    from boundless_b200.prover_server import KIND_LIFT, RECURSION_WIDTHS
+    torch, srv = gpu, small_server
+    rp = srv.opts.recursion_po2
+    words = srv.seal_words(srv._rec_circuit(KIND_LIFT))
+    bufs = [_dev_buf(torch, words) for _ in range(2)]
+    segs = [Segment(index=300 + i, po2=11 + i) for i in range(2)]
+    for slot, (seg, buf) in enumerate(zip(segs, bufs)):           # both slots in flight at once
+        srv.submit_prove_lift(slot, seg, d_out=buf.data_ptr())
+    for slot, (seg, buf) in enumerate(zip(segs, bufs)):
+        assert isinstance(srv.query(slot), bool)
+        seg_r, lift = srv.wait_task(slot)
+        ref = oracle.prove(seg.po2, seg.seed)
+        assert np.array_equal(seg_r.seal, ref)
+        d = oracle.seal_digest(ref)
+        ref_l = oracle.prove(rp, int(d[0]) | (int(d[1]) << 32), *RECURSION_WIDTHS, kind=KIND_LIFT, input_digest=d)
+        assert np.array_equal(lift.seal, ref_l)
+        assert np.array_equal(buf.cpu().numpy().view(np.uint32), ref_l)
+        assert lift.kind == KIND_LIFT and lift.claim == (seg.index, seg.index) and lift.ptr == buf.data_ptr()
+        assert srv.query(slot) is True
+
+
+def test_join_over_device_receipts_is_bit_exact_and_verifies_its_inputs(gpu, small_server, oracle):
+    """b200_recursion_verified_async = tasks::join::join (join.rs:41-79): verify left, verify right, join, verify the result, all on
+    device-resident receipts.  A corrupted input is caught by the verification inside the task ([BENTO-JOIN-003/004])."""
+    from boundless_b200 import Segment
+    from boundless_b200.prover_server import KIND_JOIN, KIND_LIFT, RECURSION_WIDTHS, DeviceReceipt, VerificationError
+    torch, srv = gpu, small_server
+    rp = srv.opts.recursion_po2
+    words = srv.seal_words(srv._rec_circuit(KIND_LIFT))
+    lifts = []
+    for i in range(2):
+        buf = _dev_buf(torch, words)
+        srv.submit_prove_lift(0, Segment(index=310 + i, po2=10), d_out=buf.data_ptr(), host_seals=False)
+        _, l = srv.wait_task(0)
+        l.owner = buf
+        assert l.seal is None
+        lifts.append(l)
+    out = _dev_buf(torch, words)
+    srv.submit_recursion_dev(1, KIND_JOIN, lifts[0], lifts[1], d_out=out.data_ptr())
+    j = srv.wait_task(1)
+    ls = [b.owner.cpu().numpy().view(np.uint32) for b in lifts]
+    d = oracle.hash_pair(oracle.seal_digest(ls[0]), oracle.seal_digest(ls[1]))
+    ref = oracle.prove(rp, int(d[0]) | (int(d[1]) << 32), *RECURSION_WIDTHS, kind=KIND_JOIN, input_digest=d)
+    assert np.array_equal(j.seal, ref) and np.array_equal(out.cpu().numpy().view(np.uint32), ref)
+    assert j.claim == (310, 311) and j.kind == KIND_JOIN
+    # device-resident verify_integrity of a device receipt
+    srv.verify_integrity(DeviceReceipt(out.data_ptr(), words, KIND_JOIN, j.claim, [], out, None))
+    # right input corrupted on the device -> the task fails in its own verification of that input, and names it
+    lifts[1].owner[words // 2] ^= 1
+    srv.submit_recursion_dev(1, KIND_JOIN, lifts[0], lifts[1], d_out=out.data_ptr())
+    with pytest.raises(VerificationError) as ei:
+        srv.wait_task(1)
+    assert ei.value.what == "right receipt" and ei.value.code != 0
+    lifts[1].owner[words // 2] ^= 1
+    # a receipt whose metadata claims another kind than its seal was proved with is rejected (header bound to the expected circuit)
+    wrong = DeviceReceipt(lifts[0].ptr, words, KIND_JOIN, lifts[0].claim, [], lifts[0].owner, None)
+    srv.submit_recursion_dev(1, KIND_JOIN, wrong, lifts[1], d_out=out.data_ptr())
+    with pytest.raises(VerificationError) as ei:
+        srv.wait_task(1)
+    assert ei.value.what == "left receipt" and ei.value.code == 103
+
+
+def test_verify_integrity_binds_the_expected_circuit(small_server, oracle):
+    """a valid seal of ANOTHER circuit / kind must not pass as the receipt it is presented as."""
+    from boundless_b200 import Segment, VerifierContext
+    from boundless_b200.prover_server import KIND_JOIN, KIND_LIFT, SegmentReceipt, SuccinctReceipt, VerificationError
+    srv = small_server
+    seg = srv.prove_segment(VerifierContext(), Segment(index=320, po2=10))
+    lifted = srv.lift(seg)
+    srv.verify_integrity(seg); srv.verify_integrity(lifted)
+    with pytest.raises(VerificationError) as ei:          # a lift seal presented as a join receipt
+        srv.verify_integrity(SuccinctReceipt(lifted.seal, KIND_JOIN, lifted.claim))
+    assert ei.value.code == 103
+    with pytest.raises(VerificationError) as ei:          # a po2-10 segment seal presented as a po2-11 one: wrong length
+        srv.verify_integrity(SegmentReceipt(seg.seal, seg.index, 11))
+    assert ei.value.code == 102
+    small = srv.prove_segment(VerifierContext(), Segment(index=321, po2=9))
+    with pytest.raises(VerificationError):                # a (valid) segment seal presented as a lift receipt
+        srv.verify_integrity(SuccinctReceipt(small.seal, KIND_LIFT, (321, 321)))
+    bad = seg.seal.copy(); bad[5] = 1                     # spare header words are bound too
+    with pytest.raises(VerificationError) as ei:
+        srv.verify_integrity(SegmentReceipt(bad, seg.index, seg.po2))
+    assert ei.value.code == 103
+
+
+def test_async_job_runner_with_real_proofs(gpu, small_server, oracle):
+    """dist.JobRunner on one GPU: 5 segments, both slots busy, joins launched as soon as their inputs exist, receipts never leave the
+    device; the root equals the oracle's evaluation of the same Planner DAG."""
+    from boundless_b200 import Segment
+    from boundless_b200.dist import B200Engine, JobRunner
+    from boundless_b200.prover_server import KIND_JOIN, KIND_LIFT, RECURSION_WIDTHS
+    torch, srv = gpu, small_server
+    rp = srv.opts.recursion_po2
+    eng = B200Engine(srv, lambda i: Segment(index=i, po2=9), torch.device("cuda", 0))
+    root, stats = JobRunner(eng, 5).run()
+    assert stats["proved"] == 5 and stats["joined"] == 4 and stats["sent"] == 0 and stats["max_in_flight"] == 2
+    assert root.claim == (0, 4)
+    def rec(kind, digest):
+        return oracle.prove(rp, int(digest[0]) | (int(digest[1]) << 32), *RECURSION_WIDTHS, kind=kind, input_digest=digest)
+    l = [rec(KIND_LIFT, oracle.seal_digest(oracle.prove(9, 0xB2000000 + i))) for i in range(5)]
+    def jn(a, b):
+        return rec(KIND_JOIN, oracle.hash_pair(oracle.seal_digest(a), oracle.seal_digest(b)))
+    want = jn(jn(jn(l[0], l[1]), jn(l[2], l[3])), l[4])          # Planner: peaks (0..3) and 4, finish joins them
+    got = eng.to_host(root)
+    assert np.array_equal(got, want)
+    assert oracle.verify(got) == 0

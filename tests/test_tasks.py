@@ -297,3 +297,99 @@ def test_bad_receipts_and_blobs_are_caught():
     job = db.create_job(execs, {"Bogus": {}}, user_id="u")
     tasks.poll_work(tasks.Agent(db, tasks.MemoryHotStore(), None, tasks.AgentArgs(task_stream=wire.EXEC_WORK_TYPE)))
     assert db.job_error(job).startswith("Invalid task_def: %s:init: unknown variant `Bogus`" % job)
+
+
+# ---- several Prove claims in flight on one GPU (poll_work_pipelined) -----------------------------------------------------------------
+class SlottedFakeProver(FakeProver):
+    """FakeProver with the asynchronous composite-task surface of ProverServer: submit_prove_lift / query / wait_task over `slots`."""
+
+    class _Opts:
+        def __init__(self, slots): self.slots = slots
+
+    def __init__(self, slots=3):
+        super().__init__()
+        self.opts = self._Opts(slots)
+        self.slot_job, self.polls, self.max_inflight = {}, {}, 0
+
+    def submit_prove_lift(self, slot, segment, d_out=0, verify=True, host_seals=True):
+        assert slot not in self.slot_job, "slot reused while busy"
+        self._maybe_fail("submit")
+        self.slot_job[slot] = segment
+        self.polls[slot] = 2 + segment.index % 3                       # completes a few polls later, out of order
+        self.max_inflight = max(self.max_inflight, len(self.slot_job))
+
+    def query(self, slot):
+        self.polls[slot] -= 1
+        return self.polls[slot] <= 0
+
+    def wait_task(self, slot):
+        from boundless_b200.prover_server import DeviceReceipt
+        segment = self.slot_job.pop(slot)
+        seg_r = self.prove_segment(None, segment)
+        if int(seg_r.seal[0]) == 0xBAD or self.fail_next.get("verify_segment", 0) > 0:
+            self.fail_next["verify_segment"] = self.fail_next.get("verify_segment", 1) - 1
+            raise VerificationError(120, "segment receipt")
+        lift = self.lift(seg_r)
+        return seg_r, DeviceReceipt(0, lift.seal.size, lift.kind, lift.claim, list(lift.assumptions), None, lift.seal)
+
+
+@pytest.mark.parametrize("n", [1, 4, 9])
+def test_pipelined_agent_gives_the_same_job_result(n):
+    """The pipelined loop claims in the same (priority, creation) order, keeps `slots` proofs in flight, stores each lifted receipt
+    before marking its task done, and the job reduces to the same root as with the synchronous loop."""
+    db, store, job, prover, exec_agent, gpu_agent, aux_agent = _run_job(n, prover=SlottedFakeProver(3))
+    tasks.poll_work(exec_agent)
+    claimed = tasks.poll_work_pipelined(gpu_agent)
+    assert claimed == n + (n - 1) + 1 and gpu_agent.errors == []
+    assert prover.max_inflight == min(3, n)
+    tasks.poll_work(aux_agent)
+    assert db.job_state(job) == "done"
+    assert not [k for k in store.kv if k.startswith("job:")]
+    root, _ = wire.deserialize_rollup(next(iter(store.assets.values())))
+    db2, store2, job2, _, e2, g2, x2 = _run_job(n)
+    tasks.poll_work(e2); tasks.poll_work(g2); tasks.poll_work(x2)
+    root2, _ = wire.deserialize_rollup(next(iter(store2.assets.values())))
+    assert np.array_equal(root.seal, root2.seal) and root.claim == root2.claim == (0, n - 1)
+
+
+def test_pipelined_agent_retries_and_fails_like_the_reference():
+    """A failed verification inside a pipelined Prove task goes through the same retry / "retry max hit" rules (lib.rs:639-677)."""
+    p = SlottedFakeProver(2)
+    db, store, job, prover, exec_agent, gpu_agent, aux_agent = _run_job(3, prover=p)
+    tasks.poll_work(exec_agent)
+    p.fail_next["verify_segment"] = 1                                  # one transient failure: retried, job still completes
+    tasks.poll_work_pipelined(gpu_agent)
+    assert len(gpu_agent.errors) == 1 and "[BENTO-WF-115] Prove failed: [BENTO-PROVE-004]" in gpu_agent.errors[0]
+    tasks.poll_work(aux_agent)
+    assert db.job_state(job) == "done"
+    p2 = SlottedFakeProver(2)
+    db, store, job, prover, exec_agent, gpu_agent, aux_agent = _run_job(2, prover=p2)
+    tasks.poll_work(exec_agent)
+    p2.fail_next["verify_segment"] = 100                               # permanent: the task exhausts its retries and fails the job
+    tasks.poll_work_pipelined(gpu_agent)
+    assert db.job_state(job) == "failed" and db.job_error(job).startswith("retry max hit: [BENTO-WF-115] Prove failed")
+
+
+def test_join_stream_mode_routes_joins_to_the_join_stream():
+    """executor.rs:517-525: with JOIN_STREAM set, join / resolve tasks are created on the customer's "join" stream; a worker on the
+    prove stream then sees Prove tasks only, one on the join stream the rest."""
+    db, prove, aux, execs = _db()
+    db.create_stream(wire.JOIN_WORK_TYPE, user_id="u")
+    store = tasks.MemoryHotStore()
+    p = SlottedFakeProver(2)
+    store.set_bytes("input:1", json.dumps({"segments": 4, "po2": 10}).encode())
+    job = db.create_job(execs, wire.task_type_to_value(wire.ExecutorReq(image=IMAGE, input="input:1", user_id="u")), user_id="u")
+    tasks.poll_work(tasks.Agent(db, store, None, tasks.AgentArgs(task_stream=wire.EXEC_WORK_TYPE, segment_po2=10, join_stream=True)))
+    prove_agent = tasks.Agent(db, store, p, tasks.AgentArgs(task_stream=wire.PROVE_WORK_TYPE))
+    assert tasks.poll_work_pipelined(prove_agent) == 4 and len(prove_agent.processed) == 4
+    assert db.job_state(job) == "running"
+    join_agent = tasks.Agent(db, store, p, tasks.AgentArgs(task_stream=wire.JOIN_WORK_TYPE))
+    assert tasks.poll_work(join_agent) == 3 + 1                          # three joins and the resolve
+    assert tasks.poll_work(tasks.Agent(db, store, p, tasks.AgentArgs(task_stream=wire.AUX_WORK_TYPE))) == 1
+    assert db.job_state(job) == "done"
+    # missing join stream is the reference's error
+    db2, _, _, execs2 = _db()
+    store2 = tasks.MemoryHotStore(); store2.set_bytes("input:1", json.dumps({"segments": 2, "po2": 10}).encode())
+    job2 = db2.create_job(execs2, wire.task_type_to_value(wire.ExecutorReq(image=IMAGE, input="input:1", user_id="u")), user_id="u")
+    tasks.poll_work(tasks.Agent(db2, store2, None, tasks.AgentArgs(task_stream=wire.EXEC_WORK_TYPE, segment_po2=10, join_stream=True)))
+    assert db2.job_state(job2) == "failed" and "missing gpu join stream" in db2.job_error(job2)
