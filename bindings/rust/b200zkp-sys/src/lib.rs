@@ -76,7 +76,20 @@ extern "C" {
     pub fn b200_prefetch_trace_async(p: *mut b200_prover, slot: u32, c: *const b200_circuit, h_trace: *const u32) -> *const c_char;
     pub fn b200_recursion_async(p: *mut b200_prover, slot: u32, c: *const b200_circuit, h_seal_a: *const u32, words_a: usize,
                                 h_seal_b: *const u32, words_b: usize, h_seal: *mut u32) -> *const c_char;
+    pub fn b200_recursion_dev_async(p: *mut b200_prover, slot: u32, c: *const b200_circuit, d_seal_a: *const u32, words_a: usize,
+                                    d_seal_b: *const u32, words_b: usize, h_seal: *mut u32) -> *const c_char;
+    // the agent's task bodies as single enqueues: tasks::prove::prover (prove.rs:44-108) and tasks::join::join (join.rs:41-79)
+    pub fn b200_prove_lift_async(p: *mut b200_prover, slot: u32, seg: *const b200_circuit, seed: u64, h_trace: *const u32,
+                                 lift: *const b200_circuit, h_seg_seal: *mut u32, h_lift_seal: *mut u32, d_lift_seal: *mut u32,
+                                 h_verdicts: *mut c_int) -> *const c_char;
+    pub fn b200_recursion_verified_async(p: *mut b200_prover, slot: u32, c: *const b200_circuit, d_seal_a: *const u32,
+                                         circuit_a: *const b200_circuit, d_seal_b: *const u32, circuit_b: *const b200_circuit,
+                                         h_seal: *mut u32, d_seal_out: *mut u32, h_verdicts: *mut c_int) -> *const c_char;
+    pub fn b200_seal_to_device(p: *mut b200_prover, slot: u32, d_dst: *mut u32, words: usize) -> *const c_char;
+    pub fn b200_prover_query(p: *mut b200_prover, slot: u32) -> c_int;
     pub fn b200_verify_async(p: *mut b200_prover, slot: u32, h_seal: *const u32, words: usize, h_result: *mut c_int) -> *const c_char;
+    pub fn b200_verify_circuit_async(p: *mut b200_prover, slot: u32, expect: *const b200_circuit, seal: *const u32, words: usize,
+                                     seal_on_device: c_int, h_result: *mut c_int) -> *const c_char;
     pub fn b200_prover_wait(p: *mut b200_prover, slot: u32) -> *const c_char;
     pub fn b200_prover_last_ms(p: *mut b200_prover, slot: u32) -> f32;
     pub fn b200_prover_mark(p: *mut b200_prover, slot: u32, which: u32) -> *const c_char;

@@ -20,6 +20,11 @@ from . import lib as _lib
 from .lib import B200Error, Circuit
 
 KIND_SEGMENT, KIND_LIFT, KIND_JOIN, KIND_RESOLVE, KIND_UNION = range(5)
+# proof-of-verifiable-work variants of the recursion programs (tasks/prove.rs:70-78 lift_povw, tasks/join_povw.rs:55 join_povw,
+# tasks/resolve_povw.rs:57 unwrap_povw): receipts whose claim is WorkClaim<ReceiptClaim>; on the synthetic path they are further
+# values of the circuit header's `kind` word, so a PoVW receipt can never be passed off as a plain one (verify_integrity binds the kind)
+KIND_LIFT_POVW, KIND_JOIN_POVW, KIND_UNWRAP_POVW = 5, 6, 7
+POVW_KINDS = (KIND_LIFT_POVW, KIND_JOIN_POVW)
 SEGMENT_WIDTHS = (16, 208, 32)       # code / data / accum
 RECURSION_WIDTHS = (16, 128, 16)     # placeholder widths of the recursion circuit (po2 = 18)
 RECURSION_PO2 = 18
@@ -221,7 +226,7 @@ class ProverServer:
             return SuccinctReceipt(seal, kind, tuple(a.claim), [x for x in a.assumptions if x != gone])
         last = b if b is not None else a
         hi = last.claim[1] if isinstance(last, SuccinctReceipt) else last.index
-        asm = list(a.assumptions) + (list(b.assumptions) if b is not None and kind == KIND_JOIN else [])
+        asm = list(a.assumptions) + (list(b.assumptions) if b is not None and kind in (KIND_JOIN, KIND_JOIN_POVW) else [])
         return SuccinctReceipt(seal, kind, (lo, hi), asm if kind != KIND_UNION else [])
 
     # -- the agent's task bodies as single enqueues (device-resident receipts) ---------------------------------------------------
@@ -391,6 +396,27 @@ class ProverServer:
 
     def union(self, a: SuccinctReceipt, b: SuccinctReceipt) -> SuccinctReceipt:
         self.submit_recursion(0, KIND_UNION, a, b)
+        return self.wait(0)
+
+    # proof-of-verifiable-work variants (POVW_LOG_ID set: workflow/src/lib.rs:209-212)
+    def lift_povw(self, receipt: SegmentReceipt) -> SuccinctReceipt:
+        """prover.lift_povw(&segment_receipt) -> SuccinctReceipt<WorkClaim<ReceiptClaim>> (tasks/prove.rs:70-78)"""
+        self.submit_recursion(0, KIND_LIFT_POVW, receipt)
+        return self.wait(0)
+
+    def join_povw(self, a: SuccinctReceipt, b: SuccinctReceipt) -> SuccinctReceipt:
+        """prover.join_povw(&left, &right) over two WorkClaim receipts (tasks/join_povw.rs:55)"""
+        for r in (a, b):
+            if r.kind not in POVW_KINDS:
+                raise B200Error("join_povw needs proof-of-verifiable-work receipts (kind %d given)" % r.kind)
+        self.submit_recursion(0, KIND_JOIN_POVW, a, b)
+        return self.wait(0)
+
+    def unwrap_povw(self, receipt: SuccinctReceipt) -> SuccinctReceipt:
+        """prover.unwrap_povw(&povw_receipt) -> SuccinctReceipt<ReceiptClaim>: drops the work claim (tasks/resolve_povw.rs:57)"""
+        if receipt.kind not in POVW_KINDS:
+            raise B200Error("unwrap_povw needs a proof-of-verifiable-work receipt (kind %d given)" % receipt.kind)
+        self.submit_recursion(0, KIND_UNWRAP_POVW, receipt)
         return self.wait(0)
 
 

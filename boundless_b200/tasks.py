@@ -91,6 +91,7 @@ class AgentArgs:
     # "join" stream instead of the prove stream, so dedicated workers can take them.  None = read the environment like the reference.
     join_stream: Optional[bool] = None
     union_stream: Optional[bool] = None
+    povw_job_number: int = 0          # WorkClaim.work.nonce_min.job of this agent's jobs (resolve_povw.rs:253-262 metadata)
 
 
 class Agent:
@@ -107,7 +108,7 @@ class Agent:
     def hot_get_bytes(self, key): return self.store.get_bytes(key)
     def hot_set_bytes(self, key, value): self.store.set_bytes(key, value)
     def hot_delete(self, key): self.store.delete(key)
-    def is_povw_enabled(self): return self.povw
+    def is_povw_enabled(self): return bool(self.povw)
 
     def _prover(self, tag):
         if self.prover is None:
@@ -124,12 +125,16 @@ def prover(agent: Agent, job_id: str, task_id: str, request: wire.ProveReq) -> L
     segment_key = "%s:%s:%d" % (job_prefix, wire.SEGMENTS_PATH, request.index)
     segment_vec = _ctx("segment data not found for segment key: %s" % segment_key, agent.hot_get_bytes, segment_key)
     segment = _ctx("Failed to deserialize segment data from redis", wire.deserialize_segment, segment_vec)
-    if agent.is_povw_enabled():
-        raise TaskError("[BENTO-PROVE-005] lift_povw is not available on this prover")
     p = agent._prover("[BENTO-PROVE-002] Missing prover from prove task")
     segment_receipt = p.prove_segment(None, segment)
     agent._verify(segment_receipt, "[BENTO-PROVE-004] Failed to verify segment receipt integrity")
     output_key = "%s:%s:%s" % (job_prefix, wire.RECUR_RECEIPT_PATH, task_id)
+    if agent.is_povw_enabled():            # prove.rs:67-93
+        lift_receipt = agent._prover("[BENTO-PROVE-005] Missing prover from resolve task").lift_povw(segment_receipt)
+        agent._verify(lift_receipt, "Failed to verify lift receipt integrity")
+        lift_asset = _ctx("Failed to serialize the POVW segment", wire.serialize_succinct, lift_receipt)
+        _ctx("Failed to set POVW receipt key with expiry", agent.hot_set_bytes, output_key, lift_asset)
+        return [segment_key]
     lift_receipt = agent._prover("[BENTO-PROVE-008] Missing prover from resolve task").lift(segment_receipt)
     agent._verify(lift_receipt, "[BENTO-PROVE-010] Failed to verify lift receipt integrity")
     lift_asset = _ctx("Failed to serialize the segment", wire.serialize_succinct, lift_receipt)
@@ -152,6 +157,24 @@ def join(agent: Agent, job_id: str, request: wire.JoinReq) -> List[str]:
     agent._verify(joined, "[BENTO-JOIN-006] Failed to verify join receipt integrity")
     blob = _ctx("Failed to serialize the joined receipt", wire.serialize_succinct, joined)
     _ctx("Failed to store joined receipt", agent.hot_set_bytes, "%s:%d" % (prefix, request.idx), blob)
+    return [left_key, right_key]
+
+
+# ---- tasks/join_povw.rs ---------------------------------------------------------------------------------------------------------
+def join_povw(agent: Agent, job_id: str, request: wire.JoinReq) -> List[str]:
+    prefix = "job:%s:%s" % (job_id, wire.RECUR_RECEIPT_PATH)
+    left_key, right_key = "%s:%d" % (prefix, request.left), "%s:%d" % (prefix, request.right)
+    left = _ctx("failed to get receipt for key: %s" % left_key, agent.hot_get_bytes, left_key)
+    right = _ctx("failed to get receipt for key: %s" % right_key, agent.hot_get_bytes, right_key)
+    left, right = wire.deserialize_succinct(left), wire.deserialize_succinct(right)
+    if agent.prover is None:
+        raise TaskError("No prover available for join task")
+    agent._verify(left, "[BENTO-JOINPOVW-001] Failed to verify left receipt integrity")
+    agent._verify(right, "[BENTO-JOINPOVW-002] Failed to verify right receipt integrity")
+    joined = _ctx("POVW join method not available - POVW functionality requires RISC Zero POVW support", agent.prover.join_povw, left, right)
+    agent._verify(joined, "[BENTO-JOINPOVW-003] Failed to verify joined POVW receipt integrity")
+    blob = _ctx("[BENTO-JOINPOVW-004] Failed to serialize joined POVW receipt", wire.serialize_succinct, joined)
+    _ctx("Failed to write joined POVW receipt to hot store", agent.hot_set_bytes, "%s:%d" % (prefix, request.idx), blob)
     return [left_key, right_key]
 
 
@@ -203,6 +226,64 @@ def resolver(agent: Agent, job_id: str, request: wire.ResolveReq):
             conditional = _ctx("Failed to resolve the conditional receipt", p.resolve, conditional, arec)
     out = _ctx("[BENTO-RESOLVE-011] Failed to serialize resolved receipt", wire.serialize_succinct, conditional)
     _ctx("Failed to set resolved receipt key with expiry", agent.hot_set_bytes, "%s:%s" % (job_prefix, wire.RESOLVED_RECEIPT_PATH), out)
+    return assumptions_len, cleanup
+
+
+# ---- tasks/resolve_povw.rs ------------------------------------------------------------------------------------------------------
+WORK_RECEIPTS_BUCKET_DIR = "work_receipts"          # workflow-common/src/storage.rs:41
+
+
+def resolve_povw(agent: Agent, job_id: str, request: wire.ResolveReq):
+    """The PoVW root is first unwrapped to a plain ReceiptClaim receipt (prover.unwrap_povw), assumptions are resolved as in
+    tasks/resolve.rs, and the ORIGINAL PoVW receipt is saved to the work-receipts bucket with its metadata (resolve_povw.rs:214-268)."""
+    import os
+    job_prefix = "job:%s" % job_id
+    receipts_key = "%s:%s" % (job_prefix, wire.RECEIPT_PATH)
+    root_key = "%s:%s:%d" % (job_prefix, wire.RECUR_RECEIPT_PATH, request.max_idx)
+    cleanup = [root_key]
+    blob = _ctx("segment data not found for root receipt key: %s" % root_key, agent.hot_get_bytes, root_key)
+    povw_receipt = _ctx("Failed to deserialize as POVW receipt", wire.deserialize_succinct, blob)
+    p = agent._prover("Missing prover for POVW resolve task")
+    conditional = _ctx("POVW unwrap failed", p.unwrap_povw, povw_receipt)
+    assumptions_len = None
+    if conditional.assumptions:
+        assumptions = list(conditional.assumptions)
+        assumptions_len = len(assumptions)
+        union_claim = ""
+        if request.union_max_idx is not None:
+            ukey = "%s:%s:%d" % (job_prefix, wire.KECCAK_RECEIPT_PATH, request.union_max_idx)
+            ublob = _ctx("Failed to get union receipt: %s" % ukey, agent.hot_get_bytes, ukey)
+            if not ublob:
+                raise TaskError("Union receipt is empty for key: %s" % ukey)
+            union_receipt = _ctx("Failed to deserialize union receipt (size: %d bytes) from key: %s" % (len(ublob), ukey),
+                                 wire.deserialize_succinct, ublob)
+            union_claim = union_receipt.claim_digest()
+            conditional = _ctx("Failed to resolve the union receipt", agent._prover("Missing prover from resolve task").resolve,
+                               conditional, union_receipt)
+        for claim in assumptions:
+            if claim == union_claim:
+                continue
+            akey = "%s:%s" % (receipts_key, claim)
+            cleanup.append(akey)
+            ablob = _ctx("corroborating receipt not found: key %s" % akey, agent.hot_get_bytes, akey)
+            if not ablob:
+                raise TaskError("Assumption receipt is empty for key: %s" % akey)
+            arec = _ctx("Failed to deserialize assumption receipt (size: %d bytes) from key: %s" % (len(ablob), akey),
+                        wire.deserialize_succinct, ablob)
+            conditional = _ctx("Failed to resolve the conditional receipt", agent._prover("Missing prover from resolve task").resolve,
+                               conditional, arec)
+    out = _ctx("Failed to serialize resolved receipt", wire.serialize_succinct, conditional)
+    _ctx("Failed to set resolved receipt key with expiry", agent.hot_set_bytes, "%s:%s" % (job_prefix, wire.RESOLVED_RECEIPT_PATH), out)
+    _ctx("Failed to save resolved POVW receipt to work receipts bucket", agent.store.write_asset,
+         "%s/%s.bincode" % (WORK_RECEIPTS_BUCKET_DIR, job_id), wire.serialize_succinct(povw_receipt))
+    meta = {"job_id": job_id}
+    if os.environ.get("POVW_LOG_ID") is not None:
+        meta["povw_log_id"] = os.environ["POVW_LOG_ID"]
+    elif isinstance(agent.povw, str):
+        meta["povw_log_id"] = agent.povw
+    meta["povw_job_number"] = str(agent.args.povw_job_number)
+    _ctx("Failed to save POVW metadata to work receipts bucket", agent.store.write_asset,
+         "%s/%s_metadata.json" % (WORK_RECEIPTS_BUCKET_DIR, job_id), json.dumps(meta).encode())
     return assumptions_len, cleanup
 
 
@@ -344,12 +425,16 @@ def process_work(agent: Agent, task: ReadyTask) -> None:
         cleanup = _ctx("[BENTO-WF-115] Prove failed", prover, agent, task.job_id, task.task_id, task_type)
         res = None
     elif isinstance(task_type, wire.JoinReq):
-        if agent.is_povw_enabled():
-            raise TaskError("[BENTO-WF-117] POVW join failed", "join_povw is not available on this prover")
-        cleanup = _ctx("[BENTO-WF-119] Join failed", join, agent, task.job_id, task_type)
+        if agent.is_povw_enabled():       # lib.rs:710-716
+            cleanup = _ctx("[BENTO-WF-117] POVW join failed", join_povw, agent, task.job_id, task_type)
+        else:
+            cleanup = _ctx("[BENTO-WF-119] Join failed", join, agent, task.job_id, task_type)
         res = None
     elif isinstance(task_type, wire.ResolveReq):
-        res, cleanup = _ctx("[BENTO-WF-123] Resolve failed", resolver, agent, task.job_id, task_type)
+        if agent.is_povw_enabled():       # lib.rs:726-734
+            res, cleanup = _ctx("[BENTO-WF-121] POVW resolve failed", resolve_povw, agent, task.job_id, task_type)
+        else:
+            res, cleanup = _ctx("[BENTO-WF-123] Resolve failed", resolver, agent, task.job_id, task_type)
     elif isinstance(task_type, wire.Finalize):
         cleanup = _ctx("[BENTO-WF-125] Finalize failed", finalize, agent, task.job_id)
         res = None

@@ -360,3 +360,37 @@ def test_async_job_runner_with_real_proofs(gpu, small_server, oracle):
     got = eng.to_host(root)
     assert np.array_equal(got, want)
     assert oracle.verify(got) == 0
+
+
+def test_povw_kinds_bit_exact(small_server, oracle):
+    """lift_povw / join_povw / unwrap_povw (tasks/prove.rs:70-78, join_povw.rs:55, resolve_povw.rs:57): recursion proofs of kinds 5, 6, 7;
+    each seal equals the oracle's for the same kind and input digest, verifies under its own kind, and is rejected under the plain one."""
+    from boundless_b200 import B200Error, Segment, VerifierContext
+    from boundless_b200.prover_server import (KIND_JOIN, KIND_JOIN_POVW, KIND_LIFT, KIND_LIFT_POVW, KIND_UNWRAP_POVW, RECURSION_WIDTHS,
+                                              SuccinctReceipt, VerificationError)
+    srv, ctx = small_server, VerifierContext()
+    rp = srv.opts.recursion_po2
+    def rec(kind, digest):
+        return oracle.prove(rp, int(digest[0]) | (int(digest[1]) << 32), *RECURSION_WIDTHS, kind=kind, input_digest=digest)
+    segs = [srv.prove_segment(ctx, Segment(index=500 + i, po2=10)) for i in range(2)]
+    lifts = [srv.lift_povw(s) for s in segs]
+    for s, l in zip(segs, lifts):
+        assert l.kind == KIND_LIFT_POVW and np.array_equal(l.seal, rec(KIND_LIFT_POVW, oracle.seal_digest(s.seal)))
+        srv.verify_integrity(l)
+        assert oracle.verify(l.seal) == 0
+    j = srv.join_povw(lifts[0], lifts[1])
+    want = rec(KIND_JOIN_POVW, oracle.hash_pair(oracle.seal_digest(lifts[0].seal), oracle.seal_digest(lifts[1].seal)))
+    assert j.kind == KIND_JOIN_POVW and j.claim == (500, 501) and np.array_equal(j.seal, want)
+    srv.verify_integrity(j)
+    u = srv.unwrap_povw(j)
+    assert u.kind == KIND_UNWRAP_POVW and u.claim == j.claim and np.array_equal(u.seal, rec(KIND_UNWRAP_POVW, oracle.seal_digest(j.seal)))
+    srv.verify_integrity(u)
+    # a PoVW receipt does not pass as a plain one, and the plain programs refuse to stand in for the PoVW ones
+    with pytest.raises(VerificationError):
+        srv.verify_integrity(SuccinctReceipt(j.seal, KIND_JOIN, j.claim))
+    plain = srv.lift(segs[0])
+    assert plain.kind == KIND_LIFT and not np.array_equal(plain.seal, lifts[0].seal)
+    with pytest.raises(B200Error):
+        srv.join_povw(plain, lifts[1])
+    with pytest.raises(B200Error):
+        srv.unwrap_povw(plain)

@@ -393,3 +393,61 @@ def test_join_stream_mode_routes_joins_to_the_join_stream():
     job2 = db2.create_job(execs2, wire.task_type_to_value(wire.ExecutorReq(image=IMAGE, input="input:1", user_id="u")), user_id="u")
     tasks.poll_work(tasks.Agent(db2, store2, None, tasks.AgentArgs(task_stream=wire.EXEC_WORK_TYPE, segment_po2=10, join_stream=True)))
     assert db2.job_state(job2) == "failed" and "missing gpu join stream" in db2.job_error(job2)
+
+
+# ---- proof-of-verifiable-work flow (POVW_LOG_ID set: lib.rs:209-212, :710-734) -----------------------------------------------------------
+class PovwFakeProver(FakeProver):
+    def lift_povw(self, r):
+        self.calls.append(("lift_povw", r.index))
+        return SuccinctReceipt(_seal("lift_povw", r.seal.tobytes()), 5, (r.index, r.index), list(r.assumptions))
+
+    def join_povw(self, a, b):
+        self._maybe_fail("join_povw")
+        self.calls.append(("join_povw", a.claim, b.claim))
+        assert a.kind in (5, 6) and b.kind in (5, 6) and a.claim[1] + 1 == b.claim[0]
+        return SuccinctReceipt(_seal("join_povw", a.seal.tobytes(), b.seal.tobytes()), 6, (a.claim[0], b.claim[1]),
+                               list(a.assumptions) + list(b.assumptions))
+
+    def unwrap_povw(self, r):
+        self.calls.append(("unwrap_povw", r.claim))
+        assert r.kind in (5, 6)
+        return SuccinctReceipt(_seal("unwrap", r.seal.tobytes()), 7, tuple(r.claim), list(r.assumptions))
+
+
+def test_povw_job_uses_the_povw_programs_end_to_end():
+    """With PoVW enabled the prove task lifts with lift_povw, joins are join_povw, resolve unwraps the root first and saves the PoVW
+    receipt + metadata to the work-receipts bucket (prove.rs:67-93, join_povw.rs, resolve_povw.rs:214-268)."""
+    db, prove, aux, execs = _db()
+    store = tasks.MemoryHotStore()
+    p = PovwFakeProver()
+    n = 5
+    store.set_bytes("input:1", json.dumps({"segments": n, "po2": 10}).encode())
+    job = db.create_job(execs, wire.task_type_to_value(wire.ExecutorReq(image=IMAGE, input="input:1", user_id="u")), user_id="u")
+    tasks.poll_work(tasks.Agent(db, store, None, tasks.AgentArgs(task_stream=wire.EXEC_WORK_TYPE, segment_po2=10)))
+    gpu_agent = tasks.Agent(db, store, p, tasks.AgentArgs(task_stream=wire.PROVE_WORK_TYPE, povw_job_number=42), povw="0x" + "ab" * 20)
+    assert tasks.poll_work(gpu_agent) == n + (n - 1) + 1 and gpu_agent.errors == []
+    tasks.poll_work(tasks.Agent(db, store, p, tasks.AgentArgs(task_stream=wire.AUX_WORK_TYPE)))
+    assert db.job_state(job) == "done"
+    names = [c[0] for c in p.calls]
+    assert names.count("lift_povw") == n and names.count("join_povw") == n - 1 and names.count("unwrap_povw") == 1
+    assert "lift" not in names and "join" not in names
+    work = wire.deserialize_succinct(store.assets["work_receipts/%s.bincode" % job])
+    assert work.kind == 6 and work.claim == (0, n - 1)                    # the PoVW root itself, not the unwrapped one
+    meta = json.loads(store.assets["work_receipts/%s_metadata.json" % job])
+    assert meta == {"job_id": job, "povw_log_id": "0x" + "ab" * 20, "povw_job_number": "42"}
+    root, _ = wire.deserialize_rollup(store.assets["receipts/stark/%s.bincode" % job])
+    assert root.kind == 7 and root.claim == (0, n - 1)                    # finalize uploads the unwrapped receipt
+
+
+def test_povw_join_failures_carry_the_reference_contexts():
+    db, prove, aux, execs = _db()
+    store = tasks.MemoryHotStore()
+    p = PovwFakeProver()
+    store.set_bytes("input:1", json.dumps({"segments": 2, "po2": 10}).encode())
+    job = db.create_job(execs, wire.task_type_to_value(wire.ExecutorReq(image=IMAGE, input="input:1", user_id="u")), user_id="u")
+    tasks.poll_work(tasks.Agent(db, store, None, tasks.AgentArgs(task_stream=wire.EXEC_WORK_TYPE, segment_po2=10, join_retries=0)))
+    agent = tasks.Agent(db, store, p, tasks.AgentArgs(task_stream=wire.PROVE_WORK_TYPE), povw=True)
+    p.fail_next["join_povw"] = 1
+    tasks.poll_work(agent)
+    assert db.job_state(job) == "failed"
+    assert db.job_error(job).startswith("[BENTO-WF-117] POVW join failed: POVW join method not available")

@@ -1,5 +1,5 @@
 """Launch each hot kernel a few times at the BASELINE shapes (16 columns x 2^20 rows) for ncu captures.
-usage: python tools/prof_kernels.py [what...]   what in {ntt, rows, rows208, fold, hal}
+usage: python tools/prof_kernels.py [what...]   what in {ntt, rows, rows208, fold, tree, hal}
 hal = K6 fri_fold, K7 batch_evaluate_any, K8 mix_poly_coeffs / eltwise_sum_extelem / poly_divide at the segment's sizes."""
 import ctypes as C
 import os
@@ -40,6 +40,16 @@ if "fold" in what:
     nodes = torch.randint(0, P, (2 * (1 << 22) * 8,), dtype=torch.int32, device="cuda")
     assert L.b200_poseidon2_fold(p(nodes), p(nodes[(1 << 22) * 8:]), 1 << 21, None) is None
     torch.cuda.synchronize()
+if "tree" in what:         # a whole 2^20-leaf Merkle tree (wide folds, the one-CTA top, the warp-form last layers) + transcript kernels via a small proof
+    lg_rows, cols = 20, 16
+    m = torch.randint(0, P, ((1 << lg_rows) * cols,), dtype=torch.int32, device="cuda")
+    nodes = torch.empty(2 * (1 << lg_rows) * 8, dtype=torch.int32, device="cuda")
+    assert L.b200_merkle_tree(p(nodes), p(m), lg_rows, cols, None) is None
+    torch.cuda.synchronize()
+    from boundless_b200 import ProverOpts, Segment, VerifierContext, get_prover_server
+    srv = get_prover_server(ProverOpts(segment_po2=12, recursion_po2=11, slots=1))
+    srv.prove_segment(VerifierContext(), Segment(index=0, po2=12))
+    srv.close()
 if "hal" in what:
     N = 1 << 20
     rnd = lambda k: torch.randint(0, P, (k,), dtype=torch.int32, device="cuda")
