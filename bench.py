@@ -227,6 +227,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pk, pk_kind = peaks()
     L = b200lib.require_gpu(local_rank)
+    # keep this rank's pinned witness buffers (and the threads touching them) on the NUMA node of its GPU
+    from boundless_b200.feed import bind_to_gpu_numa_node
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local_rank, L)
+    os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
     slots = max(1, args.slots)
     srv = get_prover_server(ProverOpts(segment_po2=PO2, segment_widths=WIDTHS, slots=slots, device=local_rank))
 
@@ -382,6 +387,23 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * args.steps / float(te[0])      # wall clock sync-to-sync: includes H2D, launches, D2H
     seal_bytes = int(rec_e.seal.size * 4)
+    # the same public-API loop fed with the compact segment descriptor (seed; witgen on the device) -- the shape of the reference's own
+    # hand-off, where a Segment of a few MB travels and the trace is expanded on the GPU (tasks/prove.rs:31-40): wall clock of the
+    # device-resident arm above.  The difference between the two end-to-end numbers is what the 940 MB/segment host trace costs.
+    e2e_desc = world * args.steps / wall_max
+    # raw pinned H2D rate of this rank alone, outside any proof: what one witness copy costs when nothing overlaps it
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dst = torch.empty(tw, dtype=torch.int32, device="cuda")
+    src_t = torch.from_numpy(traces[0][1].view(np.int32))
+    dst.copy_(src_t, non_blocking=True); torch.cuda.synchronize()
+    barrier()
+    ev0.record(); dst.copy_(src_t, non_blocking=True); ev1.record(); torch.cuda.synchronize()
+    h2d_ms = ev0.elapsed_time(ev1)
+    th = torch.tensor([h2d_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(th, op=dist.ReduceOp.MAX)
+    h2d_ms_max = float(th[0])
+    del dst
 
     # ---- BASELINE configs 3 and 4 as sub-records of the same line (every rank takes part) ----
     queue = None if args.no_job_records else queue_record(max(4, min(args.steps, 16)))
@@ -402,13 +424,20 @@ def main():
                        "witgen_standin_in_timed_region": True, "timer": "CUDA events first-launch -> last-op, max over ranks",
                        "wall_s_sync_to_sync": wall_max},
             "e2e": {"value": e2e_value, "unit": "segments/s", "h2d_bytes_per_step": tw * 4, "d2h_bytes_per_step": seal_bytes,
-                    "timer": "wall clock, sync to sync, max over ranks", "api": "ProverServer.submit_segment/prefetch_segment/wait (host trace, pinned; next witness copied under the running proof)"},
+                    "timer": "wall clock, sync to sync, max over ranks", "api": "ProverServer.submit_segment/prefetch_segment/wait (host trace, pinned; next witness copied under the running proof)",
+                    "descriptor_input": {"value": e2e_desc, "unit": "segments/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": seal_bytes,
+                                         "what": "same API and timer, input = segment descriptor (seed), witness expanded on the device"},
+                    "h2d": {"witness_copy_ms_all_ranks_at_once": h2d_ms_max, "gbs_per_gpu": tw * 4 / (h2d_ms_max * 1e-3) / 1e9,
+                            "share_of_step": h2d_ms_max / (1e3 * float(te[0]) / args.steps),
+                            "gap_vs_descriptor_input": 1.0 - e2e_value / e2e_desc},
+                    "numa": numa},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof, "roofline_int32": roof_int, "kernels": kernels,
             "queue": queue, "tree": tree,
         }
         if not args.no_cpu_baseline and world == 1:
+            os.sched_setaffinity(0, all_cpus)         # the CPU baseline uses every host core, not only the GPU's NUMA node
             os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
             from oracle import pyoracle as o          # checker / CPU baseline leg only
             o.lib()

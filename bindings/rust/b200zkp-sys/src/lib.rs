@@ -24,6 +24,7 @@ extern "C" {
     pub fn b200_init(device: c_int) -> *const c_char;
     pub fn b200_last_error() -> *const c_char;
     pub fn b200_device_count() -> c_int;
+    pub fn b200_device_pci_bus_id(device: c_int, out: *mut c_char, len: c_int) -> *const c_char;
 
     // kernel 1: NTT (sppark_batch_iNTT / _NTT / _expand / _zk_shift)
     pub fn b200_batch_intt(d_io: *mut u32, lg_n: u32, count: u32, stream: *mut c_void) -> *const c_char;

@@ -52,7 +52,7 @@ def build(force=False, verbose=False):
             print(o)
     objs = [os.path.join(OBJ, s.rsplit(".", 1)[0] + ".o") for s in SOURCES]
     if force or jobs or _stale(SO, objs):
-        run([NVCC, "-shared", "-ccbin", HOSTCXX, "-o", SO] + objs + ["-cudart", "static"])
+        run([NVCC, "-shared", "-ccbin", HOSTCXX, "-o", SO] + objs + ["-cudart", "static", "-ldl"])
     return SO
 
 

@@ -22,6 +22,15 @@ int b200_device_count(void) {
     return n;
 }
 
+// PCI bus id of a device ("0000:1b:00.0"), so that the host side can find the GPU's NUMA node in sysfs and keep its pinned witness
+// buffers on that node (boundless_b200/feed.py bind_to_gpu_numa_node)
+const char* b200_device_pci_bus_id(int device, char* out, int len) {
+    if (!out || len < 16) { set_error("b200: pci bus id buffer too small"); return last_error(); }
+    cudaError_t e = cudaDeviceGetPCIBusId(out, len, device);
+    if (e != cudaSuccess) { set_error("b200: cudaDeviceGetPCIBusId(%d): %s", device, cudaGetErrorString(e)); return last_error(); }
+    return nullptr;
+}
+
 const char* b200_init(int device) {
     int n = b200_device_count();
     if (n <= 0) { set_error("b200: no CUDA device available (this library has no CPU path)"); return last_error(); }

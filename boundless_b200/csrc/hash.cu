@@ -78,6 +78,16 @@ __global__ void __launch_bounds__(1024, 1) k_p2_fold_top(uint32_t* nodes, uint32
         __syncthreads();
     }
 }
+// one WARP per parent, any number of CTAs: the form for the narrow layers of a tree (<= 2^14 parents), where the one-thread form leaves
+// most of the chip idle and every layer costs a full single-thread permutation latency (~23 us); in warp form a layer is ~5 us.
+__global__ void __launch_bounds__(256) k_p2_fold_w(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, uint32_t n_out) {
+    P2Warp w; w.init();
+    const uint32_t i = blockIdx.x * 8u + (threadIdx.x >> 5);
+    if (i >= n_out) return;                                   // warp-uniform
+    uint32_t x = w.lane < 16 ? in[(size_t)i * 16 + w.lane] : 0u;
+    x = w.permute(x);
+    if (w.lane < 8) out[(size_t)i * 8 + w.lane] = x;
+}
 __global__ void __launch_bounds__(1024, 1) k_p2_fold_top_w(uint32_t* nodes, uint32_t top_nodes) {
     P2Warp w; w.init();
     const uint32_t wid = threadIdx.x >> 5;
@@ -117,13 +127,23 @@ cudaError_t launch_poseidon2_fold(uint32_t* d_out, const uint32_t* d_in, uint32_
 }
 cudaError_t launch_poseidon2_fold_tree(uint32_t* d_nodes, uint32_t lg_rows, cudaStream_t s) {
     if (lg_rows == 0) return cudaSuccess;
+    // wide layers: one thread per parent (throughput form).  Layers of <= 2^14 parents: one warp per parent over as many CTAs as it
+    // takes (latency form, B200_FOLD_WARP_MAX overrides the switch-over for A/B timing).  The last six layers: one CTA, no relaunch.
+    static const uint32_t warp_max = getenv("B200_FOLD_WARP_MAX") ? (uint32_t)atoi(getenv("B200_FOLD_WARP_MAX")) : (1u << 14);
     uint32_t sz = 1u << (lg_rows - 1);
-    while (sz > 1024) {
+    while (sz > 1024 && sz > warp_max) {
         cudaError_t e = launch_poseidon2_fold(d_nodes + (size_t)sz * 8, d_nodes + (size_t)sz * 16, sz, s);
         if (e != cudaSuccess) return e;
         sz >>= 1;
     }
-    if (sz >= 64) B200_LAUNCH(k_p2_fold_top)<<<1, 1024, 0, s>>>(d_nodes, sz);
+    if (warp_max >= 64) {
+        while (sz > 32) {
+            B200_LAUNCH(k_p2_fold_w)<<<(sz + 7) / 8, 256, 0, s>>>(d_nodes + (size_t)sz * 8, d_nodes + (size_t)sz * 16, sz);
+            sz >>= 1;
+        }
+    } else if (sz >= 64) {
+        B200_LAUNCH(k_p2_fold_top)<<<1, 1024, 0, s>>>(d_nodes, sz);        // round 1's one-CTA thread form (kept for the A/B)
+    }
     B200_LAUNCH(k_p2_fold_top_w)<<<1, 1024, 0, s>>>(d_nodes, sz < 32 ? sz : 32u);
     return cudaGetLastError();
 }

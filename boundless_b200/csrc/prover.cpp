@@ -8,6 +8,7 @@
 // (K1-K9) is the real work at the real shapes.
 #include "../../include/b200zkp.h"
 #include "internal.h"
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges cost nothing unless a tool (nsys, ncu --nvtx) is attached
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -17,6 +18,13 @@
 namespace b200 {
 
 static unsigned ilog2(size_t x) { unsigned r = 0; while (((size_t)1 << r) < x) r++; return r; }
+
+// NVTX range per proof phase (upstream risc0-core links nvtx for the same purpose: reference Cargo.lock:9012).  Host-side ranges around
+// the ENQUEUE of each phase; profilers attribute the kernels launched inside to the range (ncu --nvtx --nvtx-include "b200/<phase>/").
+struct Phase {
+    explicit Phase(const char* name) { nvtxRangePushA(name); }
+    ~Phase() { nvtxRangePop(); }
+};
 
 struct MerkleShape {
     uint32_t rows, cols, layers, top_layer, top_size;
@@ -191,6 +199,7 @@ static const char* prove_on_slot(b200_prover* p, Slot& s, const b200_circuit& c,
     uint32_t* code = s.coeffs; uint32_t* data = code + (size_t)c.w_code * N; uint32_t* accum = data + (size_t)c.w_data * N;
     uint32_t* ecode = s.evals; uint32_t* edata = ecode + (size_t)c.w_code * D; uint32_t* eaccum = edata + (size_t)c.w_data * D;
 
+    Phase proof_range(c.kind == 0 ? "b200/prove_segment" : "b200/recursion");
     KL(launch_iop_init(s.tr, st));
     KL(launch_iop_commit_elems(s.tr, s.seal, GLOBALS, nullptr, st));
 
@@ -202,23 +211,28 @@ static const char* prove_on_slot(b200_prover* p, Slot& s, const b200_circuit& c,
     CU(cudaMemcpyAsync(accum, data, (size_t)c.w_accum * N * 4, cudaMemcpyDeviceToDevice, st));   // raw data columns for accumulate
 
     const char* e;
-    if ((e = commit_group(p, s, code, ecode, s.nodes[0], po2, c.w_code, true, L.off_top[0]))) return e;
-    if ((e = commit_group(p, s, data, edata, s.nodes[1], po2, c.w_data, true, L.off_top[1]))) return e;
+    { Phase ph("commit_group(code)"); if ((e = commit_group(p, s, code, ecode, s.nodes[0], po2, c.w_code, true, L.off_top[0]))) return e; }
+    { Phase ph("commit_group(data)"); if ((e = commit_group(p, s, data, edata, s.nodes[1], po2, c.w_data, true, L.off_top[1]))) return e; }
 
     uint32_t* accum_mix = s.chal; uint32_t* poly_mix = s.chal + 4; uint32_t* z = s.chal + 8; uint32_t* mix = s.chal + 12;
     uint32_t* fri_mix = s.chal + 16;
-    KL(launch_iop_draw_ext(s.tr, accum_mix, 1, st));
-    KL(launch_accumulate(accum, N, c.w_accum, accum_mix, st));
-    if ((e = commit_group(p, s, accum, eaccum, s.nodes[2], po2, c.w_accum, true, L.off_top[2]))) return e;
-
-    // constraint stand-in over the 4N domain -> 4 planes x 4N -> iNTT -> 16 columns x N
-    KL(launch_iop_draw_ext(s.tr, poly_mix, 1, st));
-    KL(launch_powers(s.pmix, poly_mix, W / 4 + c.w_accum, st));
-    KL(launch_eval_check(s.check_coeffs, s.evals, po2 + 2, c.w_code, c.w_data, c.w_accum, s.pmix, st));
-    KL(launch_batch_intt(p->T, s.check_coeffs, po2 + 2, 4, st));
-    if ((e = commit_group(p, s, s.check_coeffs, s.check_evals, s.nodes[3], po2, CHECK_COLS, false, L.off_top[3]))) return e;
+    {
+        Phase ph("accumulate + commit_group(accum)");
+        KL(launch_iop_draw_ext(s.tr, accum_mix, 1, st));
+        KL(launch_accumulate(accum, N, c.w_accum, accum_mix, st));
+        if ((e = commit_group(p, s, accum, eaccum, s.nodes[2], po2, c.w_accum, true, L.off_top[2]))) return e;
+    }
+    {   // constraint stand-in over the 4N domain -> 4 planes x 4N -> iNTT -> 16 columns x N
+        Phase ph("eval_check + commit_group(check)");
+        KL(launch_iop_draw_ext(s.tr, poly_mix, 1, st));
+        KL(launch_powers(s.pmix, poly_mix, W / 4 + c.w_accum, st));
+        KL(launch_eval_check(s.check_coeffs, s.evals, po2 + 2, c.w_code, c.w_data, c.w_accum, s.pmix, st));
+        KL(launch_batch_intt(p->T, s.check_coeffs, po2 + 2, 4, st));
+        if ((e = commit_group(p, s, s.check_coeffs, s.check_evals, s.nodes[3], po2, CHECK_COLS, false, L.off_top[3]))) return e;
+    }
 
     // DEEP point and tap evaluations (K7), written straight into the seal
+    nvtxRangePushA("taps (K7) + DEEP (K8)");
     KL(launch_iop_draw_ext(s.tr, z, 1, st));
     KL(launch_deep_points(s.pts, z, p->T->rou_rev[po2], st));
     uint32_t* u = s.seal + L.off_u;
@@ -231,8 +245,10 @@ static const char* prove_on_slot(b200_prover* p, Slot& s, const b200_circuit& c,
     KL(launch_powers(s.mp, mix, T, st));
     DeepArgs da{s.coeffs, s.check_coeffs, u, s.mp, s.pts, s.combos, s.chunk_vals, s.chunk_carry, s.f_planes, po2, W, c.w_accum};
     KL(launch_deep(da, st));
+    nvtxRangePop();
 
     // FRI commit phase
+    nvtxRangePushA("FRI commit (K3, K4, K5, K6)");
     s.h_trees.clear();
     const uint32_t widths[4] = {c.w_code, c.w_data, c.w_accum, (uint32_t)CHECK_COLS};
     const uint32_t* gev[4] = {ecode, edata, eaccum, s.check_evals};
@@ -259,8 +275,10 @@ static const char* prove_on_slot(b200_prover* p, Slot& s, const b200_circuit& c,
     }
     CU(cudaMemcpyAsync(s.seal + L.off_final, cur, (size_t)4 * size * 4, cudaMemcpyDeviceToDevice, st));
     KL(launch_iop_commit_elems(s.tr, s.seal + L.off_final, 4 * size, nullptr, st));
+    nvtxRangePop();
 
     // query phase (K9)
+    Phase qph("queries (K9)");
     KL(launch_iop_draw_bits(s.tr, s.pos, QUERIES, po2 + 2, st));
     CU(cudaMemcpyAsync(s.d_trees, s.h_trees.data(), s.h_trees.size() * sizeof(GatherTree), cudaMemcpyHostToDevice, st));
     KL(launch_gather_queries(s.seal, L.off_queries, L.query_words, s.pos, s.d_trees, (uint32_t)s.h_trees.size(), st));
@@ -279,6 +297,7 @@ static const char* verify_on_slot(b200_prover* p, Slot& s, const b200_circuit& c
     const uint32_t po2 = c.po2, N = 1u << po2, D = 4 * N;
     const uint32_t W = c.w_code + c.w_data + c.w_accum, T = W + c.w_accum + CHECK_COLS;
     const SealLayout L(c);
+    Phase vrange("b200/verify_integrity");
     VerifyShape sh{};
     sh.po2 = po2; sh.w_code = c.w_code; sh.w_data = c.w_data; sh.w_accum = c.w_accum; sh.W = W; sh.T = T;
     sh.rounds = L.rounds; sh.final_size = (uint32_t)L.final_size; sh.final_lg = ilog2(L.final_size);

@@ -111,3 +111,66 @@ class PinnedRing:
         # the consumer drains prove_stream before dropping the generator, so the remaining buffers are free again
         while held:
             self.release(held.popleft())
+
+
+# ---- NUMA placement of the pinned witness buffers ---------------------------------------------------------------------------------
+def _parse_cpulist(text: str):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.extend(range(int(a), int(b) + 1))
+        else:
+            cpus.append(int(part))
+    return cpus
+
+
+def gpu_numa_node(pci_bus_id: str, sysfs: str = "/sys") -> int:
+    """NUMA node of the PCI device (sysfs numa_node), -1 when the platform does not say (single node, most VMs)."""
+    import os
+    for name in (pci_bus_id.lower(), pci_bus_id.lower().split(":", 1)[-1] if pci_bus_id.count(":") == 2 else pci_bus_id.lower()):
+        for dom in ("", "0000:"):
+            path = os.path.join(sysfs, "bus", "pci", "devices", dom + name, "numa_node")
+            try:
+                with open(path) as f:
+                    return int(f.read().strip())
+            except (OSError, ValueError):
+                continue
+    return -1
+
+
+def bind_to_gpu_numa_node(device: int, L=None, sysfs: str = "/sys") -> dict:
+    """Restrict this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned witness buffers it allocates afterwards
+    (first touch) and the threads that fill them sit next to the GPU's PCIe root: with one process per GPU (compose.yml:113) every rank
+    then streams its 940 MB witnesses from its own memory controller instead of all ranks sharing node 0.  Returns what was found and
+    done; a platform that reports no NUMA node (-1) or a single node is left alone."""
+    import os
+    from . import lib as _lib
+    L = L or _lib.load()
+    info = {"device": device, "pci_bus_id": None, "gpu_numa_node": -1, "nodes_online": None, "bound": False, "cpus": None}
+    import ctypes as C
+    buf = C.create_string_buffer(32)
+    if L.b200_device_pci_bus_id(device, buf, 32) is not None:
+        return info
+    info["pci_bus_id"] = buf.value.decode()
+    node = gpu_numa_node(info["pci_bus_id"], sysfs)
+    info["gpu_numa_node"] = node
+    try:
+        with open(os.path.join(sysfs, "devices", "system", "node", "online")) as f:
+            info["nodes_online"] = f.read().strip()
+    except OSError:
+        pass
+    if node < 0 or info["nodes_online"] in (None, "0"):
+        return info
+    try:
+        with open(os.path.join(sysfs, "devices", "system", "node", "node%d" % node, "cpulist")) as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["bound"], info["cpus"] = True, len(allowed)
+    except (OSError, ValueError):
+        pass
+    return info

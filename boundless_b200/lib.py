@@ -33,6 +33,7 @@ SYMBOLS = {
     "b200_init": (_cp, [C.c_int]),
     "b200_last_error": (_cp, []),
     "b200_device_count": (C.c_int, []),
+    "b200_device_pci_bus_id": (_cp, [C.c_int, C.c_char_p, C.c_int]),
     "b200_batch_intt": (_cp, [_vp, _u32, _u32, _vp]),
     "b200_batch_ntt": (_cp, [_vp, _u32, _u32, _vp]),
     "b200_batch_expand_ntt": (_cp, [_vp, _vp, _u32, _u32, _u32, _vp]),

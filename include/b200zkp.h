@@ -35,6 +35,8 @@ const char* b200_init(int device);
 const char* b200_last_error(void);
 /* number of CUDA devices visible, or -1 (never touches the CPU path) */
 int b200_device_count(void);
+/* PCI bus id of `device` ("0000:1b:00.0") into out[len >= 16]: lets the host side look up the GPU's NUMA node for its pinned buffers */
+const char* b200_device_pci_bus_id(int device, char* out, int len);
 /* frees the per-device twiddle tables built by b200_init (destroy every b200_prover first) */
 const char* b200_shutdown(void);
 

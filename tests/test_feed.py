@@ -94,3 +94,14 @@ def test_pinned_ring_recycles_buffers_behind_the_consumer():
     assert len(ring._free) == 4
     with pytest.raises(RuntimeError):
         ring.acquire(timeout=1)
+
+
+def test_numa_helpers_parse_sysfs(tmp_path):
+    """feed.gpu_numa_node / _parse_cpulist against a fake sysfs tree (the real lookup needs a GPU; bench.py records what it finds)."""
+    from boundless_b200 import feed
+    assert feed._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    d = tmp_path / "bus" / "pci" / "devices" / "0000:1b:00.0"
+    d.mkdir(parents=True)
+    (d / "numa_node").write_text("1\n")
+    assert feed.gpu_numa_node("0000:1B:00.0", str(tmp_path)) == 1
+    assert feed.gpu_numa_node("0000:ff:00.0", str(tmp_path)) == -1
