@@ -1094,6 +1094,18 @@ cudaError_t launch_batch_expand_ntt(const DeviceTables* T, uint32_t* d_out, cons
     const size_t N = (size_t)1 << lg_n, M = (size_t)1 << lg_m;
     if (lg_m <= 13) return run_contig<false>(T, d_out, d_in, lg_m, lg_e, 1, count, N, M, nullptr, 0, 0, 0, s);
     if (lg_m > MAX_LG) return cudaErrorInvalidValue;
+    // Column batching: the 2^lg_m-word intermediate of every column goes pass 1 -> pass 2; with `batch` columns per pair of launches it
+    // is batch * 4 * M bytes, which for small batches stays in the 126 MB L2 instead of making a round trip through HBM
+    // (B200_NTT_COLBATCH; 0 = all columns in one pair of launches).
+    const uint32_t batch = (uint32_t)env_int("B200_NTT_COLBATCH", 0);
+    if (batch > 0 && count > batch && d_out != d_in) {
+        for (uint32_t c0 = 0; c0 < count; c0 += batch) {
+            const uint32_t nb = count - c0 < batch ? count - c0 : batch;
+            cudaError_t e = launch_batch_expand_ntt(T, d_out + (size_t)c0 * M, d_in + (size_t)c0 * N, lg_n, lg_e, nb, s);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
     const uint32_t n1 = split_n1(lg_n, lg_e), n2 = lg_n - n1;
     // pass 1: row rho (N2 coefficients) -> 2^lg_e * N2 values, times w_M^(i0 * bitrev(rho))
     cudaError_t e = run_contig<false>(T, d_out, d_in, n2 + lg_e, lg_e, 1u << n1, count, N, M, T->pow_fwd[lg_m], lg_m, n1, 0, s);

@@ -87,6 +87,16 @@ struct Arena {
     uint32_t* take(size_t n) { n = (n + 63) & ~(size_t)63; uint32_t* p = base + used; used += n; return p; }
 };
 
+// Everything one verify_integrity run touches.  A slot verifies its own seal in place with `vmain` (the slot's stream and buffers); the
+// two auxiliary contexts have their own stream and buffers so that the verification of a task's INPUT receipts (tasks/join.rs:41-46)
+// and of a just-proved segment (tasks/prove.rs:56-58) runs beside the proof that follows instead of in front of it.
+struct VerifyCtx {
+    cudaStream_t stream = nullptr; cudaEvent_t ev_done = nullptr;
+    uint32_t *seal = nullptr, *chal = nullptr, *pts = nullptr, *pos = nullptr, *mp = nullptr, *pmix = nullptr, *vctx = nullptr;
+    Transcript* tr = nullptr;
+    uint32_t* alloc = nullptr;           // aux contexts: the one cudaMalloc behind the pointers above
+};
+
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_mark[2] = {nullptr, nullptr};
@@ -111,6 +121,8 @@ struct Slot {
     // verdicts travel device -> PINNED host words (a D2H copy into pageable memory would block the enqueueing thread until the stream
     // drains); b200_prover_wait hands them to the caller's ints
     int* h_vpin = nullptr; int* user_verdict[8] = {}; int n_verdicts = 0;
+    VerifyCtx vmain, vaux[2];
+    cudaEvent_t ev_fork = nullptr;
 };
 
 }  // namespace b200
@@ -166,6 +178,21 @@ static const char* slot_init(b200_prover* p, Slot& s) {
     s.d_trees = reinterpret_cast<GatherTree*>(a.take(16 * sizeof(GatherTree) / 4));
     s.vctx = a.take(VCTX_WORDS);
     if (a.used > a.words) { set_error("b200: arena overflow (%zu > %zu words)", a.used, a.words); return last_error(); }
+    s.vmain.stream = s.stream; s.vmain.seal = s.seal; s.vmain.chal = s.chal; s.vmain.pts = s.pts; s.vmain.pos = s.pos; s.vmain.mp = s.mp;
+    s.vmain.pmix = s.pmix; s.vmain.vctx = s.vctx; s.vmain.tr = s.tr;
+    CU(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+    const size_t w_seal = (SealLayout(c).total + 63) & ~(size_t)63, w_mp = (4 * (W + c.w_accum + CHECK_COLS) + 63) & ~(size_t)63,
+                 w_pmix = (4 * (W / 4 + c.w_accum) + 63) & ~(size_t)63;
+    for (auto& v : s.vaux) {
+        CU(cudaStreamCreateWithFlags(&v.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&v.ev_done, cudaEventDisableTiming));
+        const size_t words = w_seal + w_mp + w_pmix + 64 + 64 + 64 + VCTX_WORDS + sizeof(Transcript) / 4 + 64;
+        CU(cudaMalloc(&v.alloc, words * 4));
+        p->device_bytes += words * 4;
+        uint32_t* q = v.alloc;
+        v.seal = q; q += w_seal; v.mp = q; q += w_mp; v.pmix = q; q += w_pmix; v.chal = q; q += 64; v.pts = q; q += 64; v.pos = q; q += 64;
+        v.vctx = q; q += VCTX_WORDS; v.tr = reinterpret_cast<Transcript*>(q);
+    }
     return nullptr;
 }
 
@@ -292,8 +319,8 @@ static const char* prove_on_slot(b200_prover* p, Slot& s, const b200_circuit& c,
 
 // verify_integrity of the seal held in s.seal (circuit c): replay the transcript, then check the 50 queries in parallel.
 // Uses the slot's challenge / transcript scratch, so it is ordered after any proof on the same slot by the stream.
-static const char* verify_on_slot(b200_prover* p, Slot& s, const b200_circuit& c, int* h_result, bool check_header = false) {
-    cudaStream_t st = s.stream;
+static const char* verify_run(b200_prover* p, Slot& s, VerifyCtx& v, const b200_circuit& c, int* h_result, bool check_header) {
+    cudaStream_t st = v.stream;
     const uint32_t po2 = c.po2, N = 1u << po2, D = 4 * N;
     const uint32_t W = c.w_code + c.w_data + c.w_accum, T = W + c.w_accum + CHECK_COLS;
     const SealLayout L(c);
@@ -305,58 +332,83 @@ static const char* verify_on_slot(b200_prover* p, Slot& s, const b200_circuit& c
     sh.off_u = L.off_u; sh.off_final = L.off_final; sh.off_queries = L.off_queries; sh.query_words = L.query_words;
     memcpy(sh.rou_fwd, p->T->rou_fwd, sizeof sh.rou_fwd);
     sh.inv16 = h_inv(h_to_mont(16));
-    uint32_t* seal = s.seal;
-    uint32_t* accum_mix = s.chal; uint32_t* poly_mix = s.chal + 4; uint32_t* z = s.chal + 8; uint32_t* mix = s.chal + 12;
-    uint32_t* fmix = s.chal + 16;
-    uint32_t* root = s.vctx + VCTX_ROOT;
+    uint32_t* seal = v.seal;
+    uint32_t* accum_mix = v.chal; uint32_t* poly_mix = v.chal + 4; uint32_t* z = v.chal + 8; uint32_t* mix = v.chal + 12;
+    uint32_t* fmix = v.chal + 16;
+    uint32_t* root = v.vctx + VCTX_ROOT;
     const uint32_t widths[4] = {c.w_code, c.w_data, c.w_accum, (uint32_t)CHECK_COLS};
 
-    KL(launch_verify_reset(s.vctx, st));
-    if (check_header) KL(launch_verify_header(s.vctx, seal, c.po2, c.w_code, c.w_data, c.w_accum, c.kind, st));
-    KL(launch_verify_canonical(s.vctx, seal, L.total, st));
-    KL(launch_iop_init(s.tr, st));
-    KL(launch_iop_commit_elems(s.tr, seal, GLOBALS, nullptr, st));
+    KL(launch_verify_reset(v.vctx, st));
+    if (check_header) KL(launch_verify_header(v.vctx, seal, c.po2, c.w_code, c.w_data, c.w_accum, c.kind, st));
+    KL(launch_verify_canonical(v.vctx, seal, L.total, st));
+    KL(launch_iop_init(v.tr, st));
+    KL(launch_iop_commit_elems(v.tr, seal, GLOBALS, nullptr, st));
     auto commit_top = [&](uint32_t off, uint32_t rows, uint32_t cols) -> const char* {
         MerkleShape m(rows, cols);
         KL(launch_verify_fold_top(root, seal + off, m.top_size, st));
-        KL(launch_iop_commit(s.tr, root, st));
+        KL(launch_iop_commit(v.tr, root, st));
         return nullptr;
     };
     const char* e;
     if ((e = commit_top(L.off_top[0], D, widths[0]))) return e;
     if ((e = commit_top(L.off_top[1], D, widths[1]))) return e;
-    KL(launch_iop_draw_ext(s.tr, accum_mix, 1, st));          // binds the transcript; accum itself is witness
+    KL(launch_iop_draw_ext(v.tr, accum_mix, 1, st));          // binds the transcript; accum itself is witness
     if ((e = commit_top(L.off_top[2], D, widths[2]))) return e;
-    KL(launch_iop_draw_ext(s.tr, poly_mix, 1, st));
+    KL(launch_iop_draw_ext(v.tr, poly_mix, 1, st));
     if ((e = commit_top(L.off_top[3], D, widths[3]))) return e;
-    KL(launch_iop_draw_ext(s.tr, z, 1, st));
-    KL(launch_deep_points(s.pts, z, p->T->rou_rev[po2], st));
+    KL(launch_iop_draw_ext(v.tr, z, 1, st));
+    KL(launch_deep_points(v.pts, z, p->T->rou_rev[po2], st));
     const uint32_t* u = seal + L.off_u;
-    KL(launch_iop_commit_elems(s.tr, u, T * 4, nullptr, st));
-    KL(launch_powers(s.pmix, poly_mix, W / 4 + c.w_accum, st));
-    KL(launch_verify_constraint(s.vctx, u, s.pmix, z, c.w_code, c.w_data, c.w_accum, st));
-    KL(launch_iop_draw_ext(s.tr, mix, 1, st));
-    KL(launch_powers(s.mp, mix, T, st));
-    KL(launch_verify_usum(s.vctx, u, s.mp, W, c.w_accum, T, st));
+    KL(launch_iop_commit_elems(v.tr, u, T * 4, nullptr, st));
+    KL(launch_powers(v.pmix, poly_mix, W / 4 + c.w_accum, st));
+    KL(launch_verify_constraint(v.vctx, u, v.pmix, z, c.w_code, c.w_data, c.w_accum, st));
+    KL(launch_iop_draw_ext(v.tr, mix, 1, st));
+    KL(launch_powers(v.mp, mix, T, st));
+    KL(launch_verify_usum(v.vctx, u, v.mp, W, c.w_accum, T, st));
     uint32_t size = N;
     for (unsigned r = 0; r < L.rounds; r++) {
         const uint32_t rows = 4 * size / FRI_FOLD;
         MerkleShape m(rows, 4 * FRI_FOLD);
         sh.off_fri_top[r] = L.off_fri_top[r]; sh.q_off_fri[r] = L.q_off_fri[r]; sh.fri_rows[r] = rows; sh.fri_top[r] = m.top_size;
         if ((e = commit_top(L.off_fri_top[r], rows, 4 * FRI_FOLD))) return e;
-        KL(launch_iop_draw_ext(s.tr, fmix + 4 * r, 1, st));
+        KL(launch_iop_draw_ext(v.tr, fmix + 4 * r, 1, st));
         size /= FRI_FOLD;
     }
-    KL(launch_iop_commit_elems(s.tr, seal + L.off_final, 4 * size, nullptr, st));
-    KL(launch_iop_draw_bits(s.tr, s.pos, QUERIES, po2 + 2, st));
-    KL(launch_verify_queries(s.vctx, seal, sh, s.mp, s.pts, fmix, s.pos, st));
-    KL(launch_verify_finish(s.vctx, st));
+    KL(launch_iop_commit_elems(v.tr, seal + L.off_final, 4 * size, nullptr, st));
+    KL(launch_iop_draw_bits(v.tr, v.pos, QUERIES, po2 + 2, st));
+    KL(launch_verify_queries(v.vctx, seal, sh, v.mp, v.pts, fmix, v.pos, st));
+    KL(launch_verify_finish(v.vctx, st));
     if (s.n_verdicts >= 8) { set_error("b200: too many verifications pending on one slot (call b200_prover_wait)"); return last_error(); }
-    CU(cudaMemcpyAsync(&s.h_vpin[s.n_verdicts], s.vctx + VCTX_RESULT, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&s.h_vpin[s.n_verdicts], v.vctx + VCTX_RESULT, 4, cudaMemcpyDeviceToHost, st));
     s.user_verdict[s.n_verdicts++] = h_result;
     s.busy = true;
     return nullptr;
 }
+static const char* verify_on_slot(b200_prover* p, Slot& s, const b200_circuit& c, int* h_result, bool check_header = false) {
+    return verify_run(p, s, s.vmain, c, h_result, check_header);
+}
+// verify `words` words of a seal in device memory on auxiliary context k, concurrently with whatever follows on the slot's stream;
+// `after_slot`: the seal is produced on the slot's stream (the copy is ordered behind it).  join_aux() makes the slot's stream wait.
+static const char* verify_aux(b200_prover* p, Slot& s, int k, const b200_circuit& c, const uint32_t* d_seal, size_t words, bool after_slot,
+                              int* h_result) {
+    VerifyCtx& v = s.vaux[k];
+    if (after_slot) {      // the copy rides on the slot's stream: behind the proof that writes the seal, ahead of whatever overwrites it next
+        CU(cudaMemcpyAsync(v.seal, d_seal, words * 4, cudaMemcpyDeviceToDevice, s.stream));
+        CU(cudaEventRecord(s.ev_fork, s.stream));
+        CU(cudaStreamWaitEvent(v.stream, s.ev_fork, 0));
+    } else {
+        CU(cudaMemcpyAsync(v.seal, d_seal, words * 4, cudaMemcpyDeviceToDevice, v.stream));
+    }
+    const char* e = verify_run(p, s, v, c, h_result, true);
+    if (e) return e;
+    CU(cudaEventRecord(v.ev_done, v.stream));
+    return nullptr;
+}
+static const char* join_aux(Slot& s, int k) {
+    CU(cudaStreamWaitEvent(s.stream, s.vaux[k].ev_done, 0));
+    return nullptr;
+}
+
 
 // digest of a seal -> d_out8 (device): 1024-row column-major view, hash_rows, fold (K4/K5).  The seal is read from host memory
 // (staged through the slot's pinned buffer) or, with on_device, straight from caller-owned device memory (no host bounce).
@@ -425,6 +477,12 @@ void b200_prover_destroy(b200_prover* p) {
         if (s.arena.base) cudaFree(s.arena.base);
         if (s.h_stage) cudaFreeHost(s.h_stage);
         if (s.h_vpin) cudaFreeHost(s.h_vpin);
+        for (auto& v : s.vaux) {
+            if (v.stream) { cudaStreamSynchronize(v.stream); cudaStreamDestroy(v.stream); }
+            if (v.ev_done) cudaEventDestroy(v.ev_done);
+            if (v.alloc) cudaFree(v.alloc);
+        }
+        if (s.ev_fork) cudaEventDestroy(s.ev_fork);
         if (s.alt_alloc) cudaFree(s.alt_alloc);
         if (s.ev_staged) cudaEventDestroy(s.ev_staged);
         if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
@@ -551,10 +609,12 @@ const char* b200_prove_lift_async(b200_prover* p, uint32_t slot, const b200_circ
     }
     s.staged_src = nullptr; s.staged_words = 0;
     if ((e = prove_on_slot(p, s, *seg, seed, false, h_trace, h_seg_seal, staged))) return e;
-    if (h_verdicts) { h_verdicts[0] = h_verdicts[1] = -1; if ((e = verify_on_slot(p, s, *seg, &h_verdicts[0], true))) return e; }
     const size_t seg_words = SealLayout(*seg).total;
+    // the segment receipt is verified on an auxiliary stream (from a copy of the seal) WHILE the lift runs; both verdicts gate the task
+    if (h_verdicts) { h_verdicts[0] = h_verdicts[1] = -1; if ((e = verify_aux(p, s, 0, *seg, s.seal, seg_words, true, &h_verdicts[0]))) return e; }
     if ((e = recursion_on_slot(p, s, lift, s.seal, seg_words, nullptr, 0, true, h_lift_seal))) return e;
     if (h_verdicts && (e = verify_on_slot(p, s, *lift, &h_verdicts[1], true))) return e;
+    if (h_verdicts && (e = join_aux(s, 0))) return e;
     if (d_lift_seal) CU(cudaMemcpyAsync(d_lift_seal, s.seal, (size_t)SealLayout(*lift).total * 4, cudaMemcpyDeviceToDevice, s.stream));
     CU(cudaEventRecord(s.ev_end, s.stream));
     return nullptr;
@@ -581,16 +641,14 @@ const char* b200_recursion_verified_async(b200_prover* p, uint32_t slot, const b
         if (words[k] > (size_t)SealLayout(p->maxc).total || kids[k]->po2 > p->maxc.po2) { set_error("b200: child circuit exceeds the prover's max_circuit"); return last_error(); }
     }
     CU(cudaEventRecord(s.ev_begin, s.stream));
-    if (h_verdicts) {
+    if (h_verdicts) {          // left and right are verified on the two auxiliary streams, beside the join proof
         h_verdicts[0] = h_verdicts[2] = -1; h_verdicts[1] = d_b ? -1 : 0;
-        for (int k = 0; k < 2; k++) {
-            if (!kids[k]) continue;
-            CU(cudaMemcpyAsync(s.seal, seals[k], words[k] * 4, cudaMemcpyDeviceToDevice, s.stream));
-            if ((e = verify_on_slot(p, s, *kids[k], &h_verdicts[k], true))) return e;
-        }
+        for (int k = 0; k < 2; k++)
+            if (kids[k] && (e = verify_aux(p, s, k, *kids[k], seals[k], words[k], false, &h_verdicts[k]))) return e;
     }
     if ((e = recursion_on_slot(p, s, c, d_a, words[0], d_b, words[1], true, h_seal))) return e;
     if (h_verdicts && (e = verify_on_slot(p, s, *c, &h_verdicts[2], true))) return e;
+    if (h_verdicts) for (int k = 0; k < 2; k++) if (kids[k] && (e = join_aux(s, k))) return e;
     if (d_seal_out) CU(cudaMemcpyAsync(d_seal_out, s.seal, (size_t)SealLayout(*c).total * 4, cudaMemcpyDeviceToDevice, s.stream));
     CU(cudaEventRecord(s.ev_end, s.stream));
     return nullptr;
