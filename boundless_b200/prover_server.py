@@ -25,6 +25,8 @@ KIND_SEGMENT, KIND_LIFT, KIND_JOIN, KIND_RESOLVE, KIND_UNION = range(5)
 # values of the circuit header's `kind` word, so a PoVW receipt can never be passed off as a plain one (verify_integrity binds the kind)
 KIND_LIFT_POVW, KIND_JOIN_POVW, KIND_UNWRAP_POVW = 5, 6, 7
 POVW_KINDS = (KIND_LIFT_POVW, KIND_JOIN_POVW)
+KIND_KECCAK = 8        # the keccak coprocessor's proof (tasks/keccak.rs:71-75 prove_keccak); its receipts feed the union tree
+KECCAK_STATE_BYTES = 200   # [u64; 25]
 SEGMENT_WIDTHS = (16, 208, 32)       # code / data / accum
 RECURSION_WIDTHS = (16, 128, 16)     # placeholder widths of the recursion circuit (po2 = 18)
 RECURSION_PO2 = 18
@@ -310,6 +312,12 @@ class ProverServer:
         seal's header against it, so a small seal of another kind cannot pass as a lift or join receipt."""
         if isinstance(receipt, SegmentReceipt):
             return Circuit(receipt.po2, *self.opts.segment_widths, KIND_SEGMENT)
+        if receipt.kind == KIND_KECCAK:        # keccak proofs come in the size their request asked for: the seal length tells which
+            rw = self.opts.recursion_widths
+            for po2 in range(9, max(self.opts.segment_po2, self.opts.recursion_po2) + 1):
+                c = Circuit(po2, rw[0], rw[1], rw[2], KIND_KECCAK)
+                if self.seal_words(c) == int(np.asarray(receipt.seal).size):
+                    return c
         return self._rec_circuit(receipt.kind)
 
     def submit_verify(self, slot, receipt=None, expect: Optional[Circuit] = None):
@@ -397,6 +405,22 @@ class ProverServer:
     def union(self, a: SuccinctReceipt, b: SuccinctReceipt) -> SuccinctReceipt:
         self.submit_recursion(0, KIND_UNION, a, b)
         return self.wait(0)
+
+    def prove_keccak(self, claim_digest: str, po2: int, control_root: str, input_states: bytes) -> SuccinctReceipt:
+        """prover.prove_keccak(&ProveKeccakRequest{claim_digest, po2, control_root, input}) (tasks/keccak.rs:55-75), synthetic form: a
+        recursion-shaped proof of kind KIND_KECCAK with 2^po2 rows whose input digest is the digest of the keccak states (taken as
+        16-bit words, each a field element); the receipt is a SuccinctReceipt<Unknown>: no segment claim, no assumptions."""
+        if len(input_states) == 0 or len(input_states) % KECCAK_STATE_BYTES:
+            raise B200Error("keccak input must be a non-empty multiple of %d bytes" % KECCAK_STATE_BYTES)
+        rw = self.opts.recursion_widths
+        c = Circuit(int(po2), rw[0], rw[1], rw[2], KIND_KECCAK)
+        words = np.frombuffer(bytes(input_states), dtype="<u2").astype(np.uint32)
+        _lib.check(self.L.b200_recursion_async(self.h, 0, C.byref(c), words.ctypes.data_as(C.c_void_p), words.size, None, 0, self._buf(0)))
+        _lib.check(self.L.b200_prover_wait(self.h, 0))
+        seal = self._seal_bufs[0].array[: self.seal_words(c)].copy()
+        r = SuccinctReceipt(seal, KIND_KECCAK, (0, 0), [])
+        r.keccak = (claim_digest, int(po2), control_root)
+        return r
 
     # proof-of-verifiable-work variants (POVW_LOG_ID set: workflow/src/lib.rs:209-212)
     def lift_povw(self, receipt: SegmentReceipt) -> SuccinctReceipt:

@@ -178,6 +178,30 @@ def join_povw(agent: Agent, job_id: str, request: wire.JoinReq) -> List[str]:
     return [left_key, right_key]
 
 
+# ---- tasks/keccak.rs ------------------------------------------------------------------------------------------------------------
+KECCAK_STATE_BYTES = 200            # size_of::<[u64; 25]>()
+
+
+def keccak(agent: Agent, job_id: str, task_id: str, request: wire.KeccakReq) -> List[str]:
+    """The keccak coprocessor's prove task: input states from the hot store (task-scoped key, legacy key as fall-back), prove_keccak,
+    receipt to `job:{id}:keccak_receipts:{task}` where the union tree picks it up (tasks/keccak.rs:25-108)."""
+    input_path = "job:%s:%s:%s:%s" % (job_id, wire.COPROC_CB_PATH, task_id, request.claim_digest)
+    try:
+        data = agent.hot_get_bytes(input_path)
+    except Exception:                       # noqa: BLE001 -- [BENTO-KECCAK-013]: fall back to the legacy location
+        data = agent.hot_get_bytes("job:%s:%s:%s" % (job_id, wire.COPROC_CB_PATH, request.claim_digest))
+    if len(data) % KECCAK_STATE_BYTES:
+        raise TaskError("[BENTO-KECCAK-001] Input length must be a multiple of KeccakState size")
+    if not data:
+        raise TaskError("[BENTO-KECCAK-002] Received empty keccak input with claim_digest: %s" % request.claim_digest)
+    p = agent._prover("[BENTO-KECCAK-003] Missing prover from keccak prove task")
+    receipt = _ctx("Failed to prove_keccak", p.prove_keccak, request.claim_digest, request.po2, request.control_root, data)
+    blob = _ctx("[BENTO-KECCAK-005] Failed to serialize keccak receipt", wire.serialize_succinct, receipt)
+    _ctx("Failed to write keccak receipt to hot store", agent.hot_set_bytes,
+         "job:%s:%s:%s" % (job_id, wire.KECCAK_RECEIPT_PATH, task_id), blob)
+    return [input_path]
+
+
 # ---- tasks/union.rs -----------------------------------------------------------------------------------------------------------
 def union(agent: Agent, job_id: str, request: wire.UnionReq) -> List[str]:
     prefix = "job:%s:%s" % (job_id, wire.KECCAK_RECEIPT_PATH)
@@ -444,7 +468,8 @@ def process_work(agent: Agent, task: ReadyTask) -> None:
     elif isinstance(task_type, wire.SnarkReq):
         raise TaskError("[BENTO-WF-127] Snark failed", "stark2snark is out of scope for this agent")
     else:
-        raise TaskError("[BENTO-WF-129] Keccak failed", "the keccak coprocessor is out of scope for this agent")
+        cleanup = _ctx("[BENTO-WF-129] Keccak failed", keccak, agent, task.job_id, task.task_id, task_type)
+        res = None
     agent.task_db.update_task_done(task.job_id, task.task_id, res)
     # best-effort cleanup only AFTER the task is marked done, so that a retry never finds its inputs missing (lib.rs:781-797)
     for key in cleanup:

@@ -86,9 +86,9 @@ class SnarkReq:
 
 @dataclass
 class KeccakReq:
-    claim_digest: List[int]
+    claim_digest: str          # risc0 `Digest` in a human-readable format (JSON) is a 64-character hex string
     po2: int
-    control_root: List[int]
+    control_root: str
 
 
 @dataclass
@@ -126,18 +126,25 @@ def task_type_from_value(value):
         raise WireError("unknown variant `%s`" % name)
     if not isinstance(body, dict):
         raise WireError("invalid type for variant `%s`" % name)
+    # serde semantics of the reference structs (no `deny_unknown_fields`, no `#[serde(default)]`): unknown fields are IGNORED (a newer
+    # control plane may add some), every field that is not an Option is REQUIRED, a missing Option is None
     fields = cls.__dataclass_fields__
-    unknown = set(body) - set(fields)
-    missing = [f for f, spec in fields.items() if f not in body and spec.default is MISSING and spec.default_factory is MISSING]
+    optional = {"exec_limit", "union_max_idx"}
+    missing = [f for f in fields if f not in body and f not in optional]
     if missing:
         raise WireError("missing field `%s`" % missing[0])
-    if unknown:
-        raise WireError("unknown field `%s`" % sorted(unknown)[0])
+    body = {k: v for k, v in body.items() if k in fields}
     for k in ("index", "idx", "left", "right", "max_idx", "po2"):
         if k in body and (not isinstance(body[k], int) or isinstance(body[k], bool) or body[k] < 0):
             raise WireError("invalid value for `%s`" % k)
-    if "compress" in body and body["compress"] not in COMPRESS_TYPES:
-        raise WireError("unknown variant `%s`" % body["compress"])
+    for k in ("compress", "compress_type"):
+        if k in body and body[k] not in COMPRESS_TYPES:
+            raise WireError("unknown variant `%s`, expected one of `None`, `Groth16`, `Blake3Groth16`" % (body[k],))
+    for k in ("claim_digest", "control_root"):
+        if k in body:
+            v = body[k]
+            if not isinstance(v, str) or len(v) != 64 or any(c not in "0123456789abcdefABCDEF" for c in v):
+                raise WireError("invalid digest for `%s`" % k)
     return cls(**body)
 
 

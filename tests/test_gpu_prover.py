@@ -394,3 +394,32 @@ def test_povw_kinds_bit_exact(small_server, oracle):
         srv.join_povw(plain, lifts[1])
     with pytest.raises(B200Error):
         srv.unwrap_povw(plain)
+
+
+def test_prove_keccak_and_union_bit_exact(small_server, oracle):
+    """prove_keccak (tasks/keccak.rs:71-75): a kind-8 recursion-shaped proof of the requested size over the digest of the keccak input
+    states; two such receipts reduce with `union` (tasks/union.rs:43-47).  All three seals equal the oracle's."""
+    from boundless_b200 import B200Error
+    from boundless_b200.prover_server import KIND_KECCAK, KIND_UNION, RECURSION_WIDTHS
+    srv = small_server
+    rp = srv.opts.recursion_po2
+    def rec(po2, kind, digest):
+        return oracle.prove(po2, int(digest[0]) | (int(digest[1]) << 32), *RECURSION_WIDTHS, kind=kind, input_digest=digest)
+    rng = np.random.default_rng(8)
+    recs = []
+    for i, po2 in enumerate((10, 11)):
+        states = rng.integers(0, 256, 200 * (3 + i), dtype=np.uint8).tobytes()
+        r = srv.prove_keccak("%064x" % i, po2, "ee" * 32, states)
+        words = np.frombuffer(states, dtype="<u2").astype(np.uint32)
+        assert r.kind == KIND_KECCAK and np.array_equal(r.seal, rec(po2, KIND_KECCAK, oracle.seal_digest(words)))
+        srv.verify_integrity(r)
+        assert oracle.verify(r.seal) == 0
+        recs.append(r)
+    u = srv.union(recs[0], recs[1])
+    want = rec(rp, KIND_UNION, oracle.hash_pair(oracle.seal_digest(recs[0].seal), oracle.seal_digest(recs[1].seal)))
+    assert np.array_equal(u.seal, want)
+    srv.verify_integrity(u)
+    with pytest.raises(B200Error):
+        srv.prove_keccak("00" * 32, 10, "ee" * 32, b"")
+    with pytest.raises(B200Error):
+        srv.prove_keccak("00" * 32, 10, "ee" * 32, bytes(199))

@@ -81,15 +81,33 @@ def test_task_type_json_matches_serde():
     r = wire.ResolveReq(max_idx=100, union_max_idx=50)
     assert r.max_idx == 100 and r.union_max_idx == 50
     names = [wire.to_job_type_str(t) for t in (wire.ExecutorReq("i", "j", "u"), wire.ProveReq(1), wire.JoinReq(1, 2, 3), wire.ResolveReq(1),
-                                               wire.Finalize(), wire.SnarkReq("r"), wire.KeccakReq([0] * 8, 16, [0] * 8), wire.UnionReq(1, 2, 3))]
+                                               wire.Finalize(), wire.SnarkReq("r"), wire.KeccakReq("00" * 32, 16, "00" * 32), wire.UnionReq(1, 2, 3))]
     assert names == ["executor", "prove-lift", "join", "resolve", "finalize", "snark", "keccak", "union"]
 
 
-@pytest.mark.parametrize("bad", ['{"Prove":{}}', '{"Prove":{"index":-1}}', '{"Prove":{"index":1,"x":2}}', '{"Nope":{}}', '"Prove"', "[1]",
-                                 '{"Prove":{"index":1},"Join":{}}', "{", '{"Executor":{"image":"a","input":"b","user_id":"c","compress":"Zip"}}'])
+_EXEC = '"image":"a","input":"b","user_id":"c","assumptions":[],"execute_only":false'
+
+
+@pytest.mark.parametrize("bad", ['{"Prove":{}}', '{"Prove":{"index":-1}}', '{"Nope":{}}', '"Prove"', "[1]",
+                                 '{"Prove":{"index":1},"Join":{}}', "{", '{"Executor":{%s,"compress":"Zip"}}' % _EXEC,
+                                 '{"Executor":{"image":"a","input":"b","user_id":"c"}}',                  # non-Option fields are required
+                                 '{"Snark":{"receipt":"r"}}', '{"Snark":{"receipt":"r","compress_type":"Zip"}}',
+                                 '{"Keccak":{"claim_digest":[0,0],"po2":16,"control_root":"%s"}}' % ("00" * 32)])
 def test_task_type_rejects_malformed(bad):
     with pytest.raises(wire.WireError):
         wire.task_type_from_json(bad)
+
+
+def test_task_type_follows_serde_defaults():
+    """serde ignores unknown fields (no deny_unknown_fields), requires every non-Option field, treats a missing Option as
+    None; risc0 Digests are hex strings in JSON."""
+    assert wire.task_type_from_json('{"Prove":{"index":1,"added_by_a_newer_control_plane":2}}') == wire.ProveReq(1)
+    e = wire.task_type_from_json('{"Executor":{%s,"compress":"Groth16","future":true}}' % _EXEC)
+    assert e == wire.ExecutorReq("a", "b", "c", [], False, "Groth16", None)
+    assert wire.task_type_from_json('{"Resolve":{"max_idx":3}}') == wire.ResolveReq(3, None)
+    k = wire.task_type_from_json('{"Keccak":{"claim_digest":"%s","po2":17,"control_root":"%s"}}' % ("ab" * 32, "cd" * 32))
+    assert k == wire.KeccakReq("ab" * 32, 17, "cd" * 32)
+    assert wire.task_type_from_json('{"Snark":{"receipt":"r","compress_type":"Blake3Groth16"}}') == wire.SnarkReq("r", "Blake3Groth16")
 
 
 def test_bincode_blobs_roundtrip_and_layout():
@@ -451,3 +469,46 @@ def test_povw_join_failures_carry_the_reference_contexts():
     tasks.poll_work(agent)
     assert db.job_state(job) == "failed"
     assert db.job_error(job).startswith("[BENTO-WF-117] POVW join failed: POVW join method not available")
+
+
+# ---- keccak coprocessor task (tasks/keccak.rs) -----------------------------------------------------------------------------------
+class KeccakFakeProver(FakeProver):
+    def prove_keccak(self, claim_digest, po2, control_root, input_states):
+        self._maybe_fail("prove_keccak")
+        self.calls.append(("prove_keccak", claim_digest, po2, len(input_states)))
+        return SuccinctReceipt(_seal("keccak", claim_digest.encode(), bytes(input_states)), 8, (0, 0), [])
+
+
+def test_keccak_task_then_union():
+    """Two Keccak tasks prove their input states, store receipts under keccak_receipts, and the Union task joins them
+    (tasks/keccak.rs:25-108, tasks/union.rs); the error contexts are the reference's."""
+    db, prove, aux, execs = _db()
+    store = tasks.MemoryHotStore()
+    p = KeccakFakeProver()
+    coproc = db.create_stream(wire.COPROC_WORK_TYPE, user_id="u")
+    job = db.create_job(execs, wire.task_type_to_value(wire.ExecutorReq(image=IMAGE, input="x", user_id="u")), user_id="u")
+    db.update_task_done(job, INIT_TASK, None)
+    digests = ["%064x" % (i + 1) for i in range(2)]
+    for i, d in enumerate(digests):
+        db.create_task(job, str(i), coproc, wire.task_type_to_value(wire.KeccakReq(d, 17, "ee" * 32)), [], 1, 10)
+    store.set_bytes("job:%s:coproc:0:%s" % (job, digests[0]), bytes(range(200)) * 3)            # task-scoped key
+    store.set_bytes("job:%s:coproc:%s" % (job, digests[1]), bytes(200))                          # legacy key ([BENTO-KECCAK-013])
+    db.create_task(job, "2", prove, wire.task_type_to_value(wire.UnionReq(2, 0, 1)), ["0", "1"], 1, 10)
+    agent = tasks.Agent(db, store, p, tasks.AgentArgs(task_stream=wire.COPROC_WORK_TYPE))
+    assert tasks.poll_work(agent) == 2 and agent.errors == []
+    assert [c[:3] for c in p.calls if c[0] == "prove_keccak"] == [("prove_keccak", digests[0], 17), ("prove_keccak", digests[1], 17)]
+    r0 = wire.deserialize_succinct(store.get_bytes("job:%s:keccak_receipts:0" % job))
+    assert r0.kind == 8 and "job:%s:coproc:0:%s" % (job, digests[0]) not in store.kv          # input cleaned up after done
+    assert tasks.poll_work(tasks.Agent(db, store, p, tasks.AgentArgs(task_stream=wire.PROVE_WORK_TYPE))) == 1
+    u = wire.deserialize_succinct(store.get_bytes("job:%s:keccak_receipts:2" % job))
+    assert u.kind == KIND_UNION
+    # malformed inputs
+    for n, (data, tag) in enumerate([(bytes(199), "[BENTO-KECCAK-001] Input length must be a multiple of KeccakState size"),
+                                     (b"", "[BENTO-KECCAK-002] Received empty keccak input with claim_digest: " + digests[0])]):
+        tid = "k%d" % n
+        db.create_task(job, tid, coproc, wire.task_type_to_value(wire.KeccakReq(digests[0], 17, "ee" * 32)), [], 0, 10)
+        store.set_bytes("job:%s:coproc:%s:%s" % (job, tid, digests[0]), data)
+        a = tasks.Agent(db, store, p, tasks.AgentArgs(task_stream=wire.COPROC_WORK_TYPE))
+        tasks.poll_work(a)
+        assert a.errors and a.errors[0].endswith("[BENTO-WF-129] Keccak failed: " + tag), a.errors
+        db.jobs[job]["state"] = "running"          # let the next malformed case be claimed
