@@ -368,7 +368,7 @@ def main():
     # ---- end-to-end arm: witness in pinned host memory, H2D inside the timed region, seal D2H ----
     c = srv.seg_circuit
     tw = (c.w_code + c.w_data) << c.po2
-    ntr = 2
+    ntr = 5          # distinct host witnesses cycled through the e2e loop (coprime with the 4 slots: every slot sees every witness)
     pinned = []
     for k in range(ntr):
         p = C.c_void_p()

@@ -54,6 +54,9 @@ __device__ __forceinline__ uint32_t fp_sub(uint32_t a, uint32_t b) {
 // A runtime zero the compiler cannot see through (%ctaid.z of a 1-deep grid; a uniform register, read once per thread): adding it
 // makes a sum a THREE-input add, which only IADD3 (ALU pipe) can encode -- ptxas cannot turn it into IMAD.IADD (multiplier pipe).
 // Used to steer chosen adds off the multiplier pipe in the multiplier-bound kernels (B200_P2_Z in poseidon2.cuh).
+// INVARIANT: correct only in kernels launched with gridDim.z == 1, which every launch of this library is.  Since round 2
+// NO default code path uses it -- the default reduction is B200_REDC_V == 4 and the default add placement is VIADDMNMX-based
+// (B200_P2_ZALL) -- it survives only in the measured-and-rejected build variants (B200_REDC_V == 3, B200_P2_Z != 0).
 #ifdef B200_HOST_EMULATION        // tests/host_emul compiles this header for the host: the runtime zero is a plain zero there
 __device__ __forceinline__ uint32_t zreg() { return 0u; }
 #else
