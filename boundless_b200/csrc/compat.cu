@@ -97,7 +97,7 @@ sppark_error sppark_batch_expand(uint32_t* d_out, const uint32_t* d_in, uint32_t
                                  uint32_t poly_count) {
     sppark_error r;
     if (no_device(&r)) return r;
-    if (lg_domain_size + lg_blowup > (uint32_t)MAX_LG) return fail(-1, "sppark_batch_expand: expanded domain larger than 2^24");
+    if (lg_domain_size + lg_blowup > (uint32_t)MAX_LG) return fail(-1, "sppark_batch_expand: expanded domain larger than 2^26");
     if (poly_count == 0) return ok();
     const size_t total_in = (size_t)poly_count << lg_domain_size, total_out = total_in << lg_blowup;
     int dev = 0, sms = 148;

@@ -13,7 +13,9 @@ template <typename F>
 inline F* count_launch(F* f) { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); return f; }
 #define B200_LAUNCH(...) ::b200::count_launch(__VA_ARGS__)
 
-constexpr int MAX_LG = 24;          // largest transform size 2^24
+constexpr int MAX_LG = 26;          // largest transform size 2^26 (segment po2 24 x blow-up 4; upstream MAX_CYCLES_PO2 = 24)
+constexpr int MAX_LG_2PASS = 24;    // up to here a transform is two HBM passes; 2^25 and 2^26 take a third (csrc/ntt.cu)
+constexpr int BIG_N1 = 10;          // rows of the outer strided pass of the three-pass transforms
 constexpr int QUERIES = 50;
 constexpr int INV_RATE_LG = 2;      // blow-up 4
 constexpr int FRI_FOLD = 16;
@@ -31,8 +33,9 @@ struct DeviceTables {
     uint2* tw_inv;         // 8192 pairs
     // six-step inter-pass twiddle decomposition for transform size 2^m:  w_{2^m}^e = lo[e & (2^h-1)] * hi[e >> h], h = ceil(m/2)
     uint2* pow_fwd[MAX_LG + 1];      // lo (2^h) followed by hi (2^(m-h))
-    uint2* pow_inv[MAX_LG + 1];      // inverse roots; hi table pre-scaled by 2^-m (iNTT normalisation)
-    // zk_shift: 3^d = p3lo[d & 4095] * p3hi[d >> 12]
+    uint2* pow_inv[MAX_LG + 1];      // inverse roots; hi table pre-scaled by 2^-m (iNTT normalisation); for m > MAX_LG_2PASS by
+                                     // 2^-BIG_N1 only: the inner transforms of the three-pass route bring their own 2^-(m - BIG_N1)
+    // zk_shift: 3^d = p3lo[d & 4095] * p3hi[d >> 12]   (p3hi has 2^(MAX_LG - 12) entries)
     uint2* p3lo;
     uint2* p3hi;
     uint32_t rou_fwd[28], rou_rev[28];  // host copies, Montgomery

@@ -915,6 +915,28 @@ __global__ void k_zk_shift(uint32_t* __restrict__ io, uint32_t lg_n, size_t tota
     io[i] = pow_apply(io[i], p3lo[d & 4095], p3hi[d >> 12]);
 }
 
+// Inter-pass twiddle of the three-pass forward transform (sizes 2^25, 2^26): element k of row R (rho = R mod 2^lg_rows) is multiplied
+// by w_M^(k * bitrev(rho)).  In the two-pass route this multiply is fused into the contiguous pass (k_ntt_fwd1); here the contiguous
+// "pass" is itself a two-pass transform, so it is a kernel of its own (one extra trip through HBM, only for these two sizes).
+__global__ void k_ntt_row_twiddle(uint32_t* __restrict__ io, uint32_t lg_row, uint32_t lg_rows, size_t total, const tw_t* __restrict__ pow_g,
+                                  uint32_t lg_m) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= total) return;
+    const uint32_t h = (lg_m + 1) / 2, lmask = (1u << h) - 1, mmask = (1u << lg_m) - 1;
+    const tw_t* plo = pow_g; const tw_t* phi = pow_g + (1u << h);
+    const uint32_t k = (uint32_t)(i & (((size_t)1 << lg_row) - 1));
+    const uint32_t rho = (uint32_t)((i >> lg_row) & ((1u << lg_rows) - 1));
+    const uint32_t d1 = bitrev(rho, lg_rows);
+    uint4 v = *reinterpret_cast<uint4*>(io + i);
+    uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t e = (uint32_t)(((uint64_t)(k + j) * d1) & mmask);
+        x[j] = pow_apply(x[j], __ldg(plo + (e & lmask)), __ldg(phi + (e >> h)));
+    }
+    *reinterpret_cast<uint4*>(io + i) = make_uint4(x[0], x[1], x[2], x[3]);
+}
+
 __global__ void k_bit_reverse(uint32_t* __restrict__ io, uint32_t lg_n, size_t total) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -1055,6 +1077,15 @@ cudaError_t launch_batch_intt(const DeviceTables* T, uint32_t* d_io, uint32_t lg
         const uint32_t scale = h_inv(h_to_mont((uint32_t)N));
         return run_contig<true>(T, d_io, d_io, lg_n, 0, 1, count, N, N, nullptr, 0, 0, scale, s);
     }
+    if (lg_n > MAX_LG_2PASS) {
+        // three passes: the outer strided DIF over 2^BIG_N1 rows (its twiddle table carries 1/2^BIG_N1), then every contiguous row of
+        // 2^(lg_n - BIG_N1) values is an inverse transform of its own (two passes, carrying the rest of the normalisation)
+        const uint32_t n2 = lg_n - BIG_N1;
+        if ((uint64_t)count << BIG_N1 > 0xffffffffull) return cudaErrorInvalidValue;
+        cudaError_t e = run_strided<true>(T, d_io, BIG_N1, 1u << n2, 1u << n2, count, N, T->pow_inv[lg_n], lg_n, s);
+        if (e != cudaSuccess) return e;
+        return launch_batch_intt(T, d_io, n2, count << BIG_N1, s);
+    }
     const uint32_t n1 = split_n1(lg_n), n2 = lg_n - n1;
     // pass A: DIF over i1 (rows of stride N2) + twiddle (1/N folded into the table)
     cudaError_t e = run_strided<true>(T, d_io, n1, 1u << n2, 1u << n2, count, N, T->pow_inv[lg_n], lg_n, s);
@@ -1071,6 +1102,10 @@ cudaError_t launch_batch_intt_shift(const DeviceTables* T, uint32_t* d_io, uint3
     const size_t N = (size_t)1 << lg_n;
     bool done = false;
     cudaError_t e;
+    if (lg_n > MAX_LG_2PASS) {          // three-pass sizes: the coset shift is a pass of its own
+        e = launch_batch_intt(T, d_io, lg_n, count, s);
+        return e != cudaSuccess ? e : launch_zk_shift(T, d_io, lg_n, count, s);
+    }
     if (lg_n <= 12) {
         const uint32_t scale = h_inv(h_to_mont((uint32_t)N));
         e = run_contig<true>(T, d_io, d_io, lg_n, 0, 1, count, N, N, nullptr, 0, 0, scale, s, T->p3lo, T->p3hi, &done);
@@ -1090,10 +1125,22 @@ cudaError_t launch_batch_expand_ntt(const DeviceTables* T, uint32_t* d_out, cons
     const uint32_t lg_m = lg_n + lg_e;
     if (lg_m == 0)        // size-1 transforms are the identity
         return d_out == d_in ? cudaSuccess : cudaMemcpyAsync(d_out, d_in, (size_t)count * 4, cudaMemcpyDeviceToDevice, s);
-    if (lg_m > MAX_LG + 2) return cudaErrorInvalidValue;
     const size_t N = (size_t)1 << lg_n, M = (size_t)1 << lg_m;
     if (lg_m <= 13) return run_contig<false>(T, d_out, d_in, lg_m, lg_e, 1, count, N, M, nullptr, 0, 0, 0, s);
     if (lg_m > MAX_LG) return cudaErrorInvalidValue;
+    if (lg_m > MAX_LG_2PASS) {
+        // three passes: every row of 2^(lg_n - BIG_N1) coefficients is a forward transform of its own (expand included), then the
+        // inter-pass twiddle, then the strided DIT over the 2^BIG_N1 rows
+        if (lg_n <= (uint32_t)BIG_N1 || (uint64_t)count << BIG_N1 > 0xffffffffull) return cudaErrorInvalidValue;
+        const uint32_t n2 = lg_n - BIG_N1, lg_row = n2 + lg_e;
+        cudaError_t e = launch_batch_expand_ntt(T, d_out, d_in, n2, lg_e, count << BIG_N1, s);
+        if (e != cudaSuccess) return e;
+        const size_t total = (size_t)count << lg_m;
+        B200_LAUNCH(k_ntt_row_twiddle)<<<(unsigned)((total / 4 + 255) / 256), 256, 0, s>>>(d_out, lg_row, BIG_N1, total, T->pow_fwd[lg_m], lg_m);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        return run_strided<false>(T, d_out, BIG_N1, 1u << lg_row, 1u << lg_row, count, M, nullptr, 0, s);
+    }
     // Column batching: the 2^lg_m-word intermediate of every column goes pass 1 -> pass 2; with `batch` columns per pair of launches it
     // is batch * 4 * M bytes, which for small batches stays in the 126 MB L2 instead of making a round trip through HBM
     // (B200_NTT_COLBATCH; 0 = all columns in one pair of launches).

@@ -43,7 +43,7 @@ static unsigned fri_rounds(unsigned po2, size_t* final_size) {
 
 static const char* check_circuit(const b200_circuit* c) {
     if (!c) return "b200: null circuit";
-    if (c->po2 < 9 || c->po2 > 22) return "b200: po2 out of range [9,22]";
+    if (c->po2 < 9 || c->po2 > 24) return "b200: po2 out of range [9,24]";
     if (c->w_code == 0 || c->w_code % 4 || c->w_data % 4 || c->w_accum % 4 || c->w_accum == 0)
         return "b200: column widths must be positive multiples of 4";
     if (c->w_accum > c->w_data) return "b200: w_accum must not exceed w_data";

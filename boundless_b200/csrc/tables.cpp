@@ -86,7 +86,8 @@ const DeviceTables* get_tables(int device) {
             uint32_t cur = h_to_mont(1);
             for (uint32_t i = 0; i < (1u << h); i++) { t[i] = cur; cur = h_mul(cur, w); }
             const uint32_t wh = h_pow(w, (uint64_t)1 << h);
-            cur = inv ? h_inv(h_to_mont(1u << m)) : h_to_mont(1);      // fold 1/2^m into the inverse hi table
+            // fold the normalisation into the inverse hi table: 1/2^m, or 1/2^BIG_N1 for the sizes that take the three-pass route
+            cur = inv ? h_inv(h_to_mont(1u << (m > MAX_LG_2PASS ? BIG_N1 : m))) : h_to_mont(1);
             for (uint32_t i = 0; i < (1u << (m - h)); i++) { t[((size_t)1 << h) + i] = cur; cur = h_mul(cur, wh); }
             uint2* d = upload(t);
             ok &= d != nullptr;
@@ -95,12 +96,12 @@ const DeviceTables* get_tables(int device) {
     }
     // zk_shift tables
     {
-        std::vector<uint32_t> lo(4096), hi(4096);
+        std::vector<uint32_t> lo(4096), hi((size_t)1 << (MAX_LG - 12));
         const uint32_t three = h_to_mont(3), step = h_pow(three, 4096);
         uint32_t cur = h_to_mont(1);
         for (int i = 0; i < 4096; i++) { lo[i] = cur; cur = h_mul(cur, three); }
         cur = h_to_mont(1);
-        for (int i = 0; i < 4096; i++) { hi[i] = cur; cur = h_mul(cur, step); }
+        for (size_t i = 0; i < hi.size(); i++) { hi[i] = cur; cur = h_mul(cur, step); }
         T->p3lo = upload(lo); T->p3hi = upload(hi);
         ok &= T->p3lo && T->p3hi;
     }

@@ -41,7 +41,8 @@ const char* b200_device_pci_bus_id(int device, char* out, int len);
 const char* b200_shutdown(void);
 
 /* ---- kernel 1: NTT (replaces sppark_batch_iNTT / _NTT / _expand / _zk_shift) ------------------------------ */
-/* K1: `count` in-place iNTTs of size 2^lg_n: natural-order evaluations -> bit-reversed coefficients, x 2^-lg_n */
+/* Transform sizes up to 2^26 (a po2-24 segment at blow-up 4; upstream MAX_CYCLES_PO2 = 24): two HBM passes up to 2^24, three above.
+ * K1: `count` in-place iNTTs of size 2^lg_n: natural-order evaluations -> bit-reversed coefficients, x 2^-lg_n */
 const char* b200_batch_intt(uint32_t* d_io, uint32_t lg_n, uint32_t count, void* stream);
 /* forward: bit-reversed coefficients -> natural-order evaluations, in place */
 const char* b200_batch_ntt(uint32_t* d_io, uint32_t lg_n, uint32_t count, void* stream);
@@ -107,7 +108,7 @@ const char* b200_commit_group(uint32_t* d_coeffs_io, uint32_t* d_evals, uint32_t
 
 /* ---- prover pipeline (the ProverServer operator boundary) ------------------------------------------------------- */
 typedef struct {
-    uint32_t po2;                       /* trace rows = 2^po2; reference default 20 (workflow/src/lib.rs:83-84) */
+    uint32_t po2;                       /* trace rows = 2^po2, 9..24; reference default 20 (workflow/src/lib.rs:83-84) */
     uint32_t w_code, w_data, w_accum;   /* synthetic column-group widths; segment default 16/208/32 */
     uint32_t kind;                      /* 0 segment, 1 lift, 2 join, 3 resolve, 4 union */
 } b200_circuit;

@@ -185,7 +185,7 @@ static void commit_group(iop_t *io, group_t *g, unsigned po2, int do_interp_shif
 static void group_free(group_t *g) { free(g->coeffs); free(g->evals); free(g->nodes); }
 
 static int check_circuit(const oracle_circuit *c) {
-    if (c->po2 < 9 || c->po2 > 22) return 1;
+    if (c->po2 < 9 || c->po2 > 24) return 1;          /* upstream MAX_CYCLES_PO2 = 24 */
     if (c->w_code == 0 || c->w_code % 4 || c->w_data % 4 || c->w_accum % 4 || c->w_accum == 0) return 1;
     if (c->w_accum > c->w_data) return 1;
     if (c->w_code + c->w_data + c->w_accum > 512) return 1;

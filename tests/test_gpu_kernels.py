@@ -66,7 +66,7 @@ def test_batch_intt_and_shift(gpu, b200lib, oracle, lg_n, count):
     assert np.array_equal(host(d2), shifted)
 
 
-@pytest.mark.parametrize("lg_n,count", [(1, 2), (5, 3), (10, 4), (12, 5), (13, 2), (14, 3), (16, 4), (17, 2), (19, 2), (20, 2), (21, 1), (22, 1), (23, 1), (24, 1)])
+@pytest.mark.parametrize("lg_n,count", [(1, 2), (5, 3), (10, 4), (12, 5), (13, 2), (14, 3), (16, 4), (17, 2), (19, 2), (20, 2), (21, 1), (22, 1), (23, 1), (24, 1), (25, 1), (26, 1)])
 def test_batch_ntt_roundtrip(gpu, b200lib, oracle, lg_n, count):
     torch = gpu
     rng = np.random.default_rng(7 + lg_n)
@@ -219,8 +219,8 @@ def test_empty_and_out_of_range_inputs(gpu, b200lib, oracle):
     ck(b200lib.b200_fri_fold(ptr(d), ptr(d), 8, ptr(d), None))          # fewer than 16 coefficients: nothing to fold
     torch.cuda.synchronize()
     assert int(d.abs().sum()) == 0
-    assert b200lib.b200_batch_intt(ptr(d), 25, 1, None) is not None     # > 2^24
-    assert b200lib.b200_batch_expand_ntt(ptr(d), ptr(d), 23, 2, 1, None) is not None
+    assert b200lib.b200_batch_intt(ptr(d), 27, 1, None) is not None     # > 2^26
+    assert b200lib.b200_batch_expand_ntt(ptr(d), ptr(d), 25, 2, 1, None) is not None
     assert b200lib.b200_merkle_tree(ptr(d), ptr(d), 27, 1, None) is not None
     # size-1 transforms are the identity
     one = dev(torch, oracle.to_mont(np.array([5, 7, 11])))
@@ -275,6 +275,20 @@ def test_merkle_tree_full_size(gpu, b200lib, oracle):
     assert np.array_equal(host(d_nodes)[8:], ref[8:])
 
 
+@pytest.mark.parametrize("lg_n,count", [(23, 2), (24, 1), (21, 3)])
+def test_batch_expand_ntt_three_pass_sizes(gpu, b200lib, oracle, lg_n, count):
+    """K3 for po2 23 / 24 segments: 2^23 -> 2^25 and 2^24 -> 2^26 evaluations (three-pass route: a complete expand + NTT per row of the
+    outer split, the inter-pass twiddle as its own kernel, the strided pass), and (21 -> 23) as the largest two-pass neighbour."""
+    torch = gpu
+    d_in, a = dev_rand(torch, count << lg_n, 3000 + lg_n)
+    d_out = torch.zeros(count << (lg_n + 2), dtype=torch.int32, device="cuda")
+    ck(b200lib.b200_batch_expand_ntt(ptr(d_out), ptr(d_in), lg_n, 2, count, None))
+    torch.cuda.synchronize()
+    got = host(d_out)
+    del d_in, d_out
+    assert np.array_equal(got, oracle.batch_expand_ntt(a, lg_n, count, 2))
+
+
 @pytest.mark.parametrize("count", [16, 272])
 def test_batch_expand_ntt_full_size(gpu, b200lib, oracle, count):
     """K3 at the headline shape: 2^20 coefficients -> 2^22 evaluations, 16 columns (one launch group) and all 272 columns of a segment."""
@@ -289,10 +303,11 @@ def test_batch_expand_ntt_full_size(gpu, b200lib, oracle, count):
     assert np.array_equal(got, oracle.batch_expand_ntt(a, lg_n, count, 2))
 
 
-@pytest.mark.parametrize("lg_n,count", [(20, 272), (22, 4), (23, 2), (24, 2)])
+@pytest.mark.parametrize("lg_n,count", [(20, 272), (22, 4), (23, 2), (24, 2), (25, 2), (26, 1)])
 def test_batch_intt_large_against_the_oracle(gpu, b200lib, oracle, lg_n, count):
-    """K1 (+K2 fused) against the oracle at the headline shape (272 x 2^20) and at lg_n 22-24 (the check-polynomial iNTT is 2^22;
-    upstream MAX_CYCLES_PO2 = 24), not only as a round trip."""
+    """K1 (+K2 fused) against the oracle at the headline shape (272 x 2^20) and at lg_n 22-26, not only as a round trip: 2^22 is the
+    check-polynomial iNTT of a 2^20 segment; 2^25 and 2^26 (the evaluation domains of po2 23 / 24, upstream MAX_CYCLES_PO2 = 24) take
+    the three-pass route (outer strided pass + a complete inner transform per row)."""
     torch = gpu
     d, a = dev_rand(torch, count << lg_n, 100 * lg_n + count)
     d2 = d.clone()

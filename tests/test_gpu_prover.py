@@ -232,6 +232,42 @@ def test_full_size_segment_is_deterministic_and_lifts(full_server, oracle):
     assert oracle.verify(l0.seal) == 0
 
 
+def test_po2_22_segment_bit_exact(gpu, oracle):
+    """The first size whose evaluation matrix exceeds 2^32 words (272 columns x 2^24): every word of the seal against the oracle."""
+    from boundless_b200 import ProverOpts, Segment, VerifierContext, get_prover_server
+    srv = get_prover_server(ProverOpts(segment_po2=22, recursion_po2=18, slots=1))
+    try:
+        seg = Segment(index=22, po2=22)
+        r = srv.prove_segment(VerifierContext(), seg)
+        ref = oracle.prove(22, seg.seed)
+        assert np.array_equal(r.seal, ref)
+        srv.verify_integrity(r)
+    finally:
+        srv.close()
+
+
+@pytest.mark.parametrize("po2", [23, 24])
+def test_po2_23_24_segments_verify(gpu, oracle, po2):
+    """Upstream MAX_CYCLES_PO2 = 24: segments of 2^23 and 2^24 rows (evaluation domains 2^25 / 2^26: three-pass transforms, Merkle
+    trees of 2^25 / 2^26 leaves, 55 / 111 GB of device memory for the one slot).  The oracle's PROVER is not run at these sizes (its
+    evaluation matrix alone is 37 / 73 GB of host memory); the seal must pass the oracle's verifier and the device verifier, be
+    deterministic, and the kernels underneath are compared with the oracle at these sizes in tests/test_gpu_kernels.py."""
+    from boundless_b200 import ProverOpts, Segment, VerifierContext, get_prover_server
+    srv = get_prover_server(ProverOpts(segment_po2=po2, recursion_po2=18, slots=1))
+    try:
+        seg = Segment(index=po2, po2=po2)
+        r = srv.prove_segment(VerifierContext(), seg)
+        assert r.seal.size == oracle.seal_words(po2)
+        assert oracle.verify(r.seal) == 0
+        srv.verify_integrity(r)
+        if po2 == 23:
+            assert np.array_equal(srv.prove_segment(VerifierContext(), seg).seal, r.seal)
+            l = srv.lift(r)
+            assert oracle.verify(l.seal) == 0
+    finally:
+        srv.close()
+
+
 def test_po2_21_segment_verifies(gpu, oracle):
     """compose.yml:67 runs the agents with --segment-po2 21: one 2^21-row segment (twice BASELINE config 2; 2^23-point evaluation
     domain, 2^23-leaf Merkle trees, the 2^23 check-polynomial iNTT) must pass the oracle's verifier."""
