@@ -49,7 +49,7 @@ def test_seal_layout_matches_oracle(b200lib, oracle, circ):
 
 def test_circuit_validation(b200lib):
     from boundless_b200 import Circuit
-    for bad in [(8, 16, 32, 8, 0), (23, 16, 32, 8, 0), (10, 0, 32, 8, 0), (10, 16, 30, 8, 0), (10, 16, 8, 16, 0), (10, 16, 500, 8, 0)]:
+    for bad in [(8, 16, 32, 8, 0), (25, 16, 32, 8, 0), (10, 0, 32, 8, 0), (10, 16, 30, 8, 0), (10, 16, 8, 16, 0), (10, 16, 500, 8, 0)]:
         assert b200lib.b200_seal_words(C.byref(Circuit(*bad))) == 0
 
 
