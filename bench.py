@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--mode", default="segments", choices=["segments", "tree"],
                     help="segments: BASELINE configs 2/3 (default, the contract line); tree: config 4, prove+lift+join to one root")
     ap.add_argument("--segments-per-gpu", type=int, default=4, help="tree mode: segments per rank")
+    ap.add_argument("--tree-seg-in-flight", type=int, default=0, help="tree: Prove tasks in flight per GPU (0 = JobRunner default, every slot)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -254,7 +255,7 @@ def main():
         n_seg = segs_per_gpu * world
         barrier()
         t0 = time.perf_counter()
-        root, stats = JobRunner(eng, n_seg).run()
+        root, stats = JobRunner(eng, n_seg, max_segments_in_flight=args.tree_seg_in_flight or None).run()
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt, float(stats["bytes_sent"]), float(stats["sent"]), float(stats["max_in_flight"])], dtype=torch.float64, device="cuda")
@@ -269,6 +270,7 @@ def main():
         return {"segments": n_seg, "segments_per_gpu": segs_per_gpu, "ms_to_root": float(tt[0]) * 1e3,
                 "segments_per_sec_to_root": n_seg / float(tt[0]), "joins": n_seg - 1, "lifts": n_seg,
                 "nccl_bytes_moved": int(tt[1]), "nccl_transfers": int(tt[2]), "max_tasks_in_flight_per_gpu": int(tt[3]),
+                "prove_tasks_in_flight_per_gpu": args.tree_seg_in_flight or slots,
                 "root_claim": list(root.claim), "root_kind": "join" if root.kind == KIND_JOIN else "lift", "root_verifies": True,
                 "verify_after_every_step": True, "recursion_po2": srv.opts.recursion_po2,
                 "exchange": "device tensors, torch.distributed isend/irecv (NCCL) announced over a gloo control group; no host bounce",

@@ -161,7 +161,7 @@ def _async_worker(rank, world, port, n_segments, q):
     try:
         lo, hi = shard_bounds(n_segments, rank, world)
         eng = _StubEngine(3, lo, hi)
-        root, stats = JobRunner(eng, n_segments).run()
+        root, stats = JobRunner(eng, n_segments, max_segments_in_flight=2).run()
         q.put((rank, None if root is None else (root.owner.numpy().view(np.uint32).tobytes(), root.claim), stats, eng.proved, eng.max_running))
     finally:
         dist.destroy_process_group()
@@ -199,7 +199,19 @@ def test_async_job_runner_single_process(b200lib):
     sys.path.insert(0, ROOT)
     from boundless_b200.dist import JobRunner
     eng = _StubEngine(3, 0, 9)
-    root, stats = JobRunner(eng, 9).run()
+    root, stats = JobRunner(eng, 9, max_segments_in_flight=3).run()
     assert root.claim == (0, 8) and stats["proved"] == 9 and stats["joined"] == 8 and stats["sent"] == 0
     assert root.owner.numpy().view(np.uint32).tobytes() == _expected_root(9).tobytes()
     assert eng.max_running == 3
+    # max_segments_in_flight caps the Prove tasks that run at once (the other slots are kept for lifts and joins); same root
+    eng2 = _StubEngine(4, 0, 9)
+    seg_running = []
+    orig_submit, orig_finish = eng2.submit_segment, eng2.finish
+    live = set()
+    def submit_segment(slot, index, out):
+        live.add(slot); seg_running.append(len(live)); orig_submit(slot, index, out)
+    def finish(slot):
+        live.discard(slot); return orig_finish(slot)
+    eng2.submit_segment, eng2.finish = submit_segment, finish
+    root2, _ = JobRunner(eng2, 9, max_segments_in_flight=2).run()
+    assert max(seg_running) == 2 and root2.owner.numpy().view(np.uint32).tobytes() == _expected_root(9).tobytes()
