@@ -146,7 +146,8 @@ class B200Engine:
         self.slots = srv.opts.slots
         self.words = srv.seal_words(srv._rec_circuit(KIND_LIFT))
         self.KIND_JOIN = KIND_JOIN
-        self._pool = []
+        self._pool = []            # receipt buffers returned by release(), reused by new_buffer()
+        self._out = {}             # slot -> the buffer its running task writes its receipt to
 
     def new_buffer(self):
         return self._pool.pop() if self._pool else self.torch.empty(self.words, dtype=self.torch.int32, device=self.device)
@@ -161,7 +162,7 @@ class B200Engine:
 
     def submit_segment(self, slot, index, out):
         self.srv.submit_prove_lift(slot, self.make_segment(index), d_out=out.data_ptr(), verify=self.verify, host_seals=False)
-        self._out = getattr(self, "_out", {}); self._out[slot] = out
+        self._out[slot] = out
 
     def submit_join(self, slot, a, b, out):
         self.srv.submit_recursion_dev(slot, self.KIND_JOIN, a, b, d_out=out.data_ptr(), verify=self.verify, host_seal=False)
