@@ -76,8 +76,8 @@ def test_expand_then_ntt_is_the_low_degree_extension(gpu, b200lib, oracle, lg_n,
 
 def test_expand_rejects_oversize(gpu, b200lib):
     from boundless_b200 import lib
-    err = b200lib.sppark_batch_expand(None, None, 23, 2, 1)
-    with pytest.raises(lib.B200Error, match="2\\^24"):
+    err = b200lib.sppark_batch_expand(None, None, 25, 2, 1)          # 2^27 > 2^26, the largest transform (po2 24 x blow-up 4)
+    with pytest.raises(lib.B200Error, match="2\\^26"):
         lib.check_sppark(err)
 
 
