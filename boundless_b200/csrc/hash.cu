@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(1024, 1) k_p2_fold_top(uint32_t* nodes, uint32
         __syncthreads();
     }
 }
-// one WARP per parent, any number of CTAs: the form for the narrow layers of a tree (<= 2^14 parents), where the one-thread form leaves
+// one WARP per parent, any number of CTAs: the form for the narrow layers of a tree (<= 2^12 parents), where the one-thread form leaves
 // most of the chip idle and every layer costs a full single-thread permutation latency (~23 us); in warp form a layer is ~5 us.
 __global__ void __launch_bounds__(256) k_p2_fold_w(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, uint32_t n_out) {
     P2Warp w; w.init();
@@ -127,9 +127,10 @@ cudaError_t launch_poseidon2_fold(uint32_t* d_out, const uint32_t* d_in, uint32_
 }
 cudaError_t launch_poseidon2_fold_tree(uint32_t* d_nodes, uint32_t lg_rows, cudaStream_t s) {
     if (lg_rows == 0) return cudaSuccess;
-    // wide layers: one thread per parent (throughput form).  Layers of <= 2^14 parents: one warp per parent over as many CTAs as it
-    // takes (latency form, B200_FOLD_WARP_MAX overrides the switch-over for A/B timing).  The last six layers: one CTA, no relaunch.
-    static const uint32_t warp_max = getenv("B200_FOLD_WARP_MAX") ? (uint32_t)atoi(getenv("B200_FOLD_WARP_MAX")) : (1u << 14);
+    // wide layers: one thread per parent (throughput form).  Layers of <= 2^12 parents: one warp per parent over as many CTAs as it
+    // takes (latency form; measured cross-over, profiles/ncu_brief_r02_round2_kernels.txt: 17 us against ~25 us at 4096 parents, but
+    // 26 / 47 us at 8192 / 16384; B200_FOLD_WARP_MAX overrides it for A/B timing).  The last six layers: one CTA, no relaunch.
+    static const uint32_t warp_max = getenv("B200_FOLD_WARP_MAX") ? (uint32_t)atoi(getenv("B200_FOLD_WARP_MAX")) : (1u << 12);
     uint32_t sz = 1u << (lg_rows - 1);
     while (sz > 1024 && sz > warp_max) {
         cudaError_t e = launch_poseidon2_fold(d_nodes + (size_t)sz * 8, d_nodes + (size_t)sz * 16, sz, s);
