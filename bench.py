@@ -408,8 +408,16 @@ def main():
     del dst
 
     # ---- BASELINE configs 3 and 4 as sub-records of the same line (every rank takes part) ----
-    queue = None if args.no_job_records else queue_record(max(4, min(args.steps, 16)))
-    tree = None if args.no_job_records else tree_record(args.segments_per_gpu)
+    def guarded(fn, *a):
+        """A failure in a job record must not take the contract line with it: record it instead (every rank runs the same code, so a
+        deterministic failure is caught on all of them and the run stays in step)."""
+        try:
+            return fn(*a)
+        except Exception as e:          # noqa: BLE001
+            torch.cuda.synchronize()
+            return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+    queue = None if args.no_job_records else guarded(queue_record, max(4, min(args.steps, 16)))
+    tree = None if args.no_job_records else guarded(tree_record, args.segments_per_gpu)
 
     out = None
     if rank == 0:
