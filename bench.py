@@ -215,6 +215,7 @@ def main():
     # keep stdout clean for the single JSON line: NCCL / library banners go to stderr until the result is printed
     real_stdout = os.dup(1)
     os.dup2(2, 1)
+    os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")   # the tree record uses unbatched isend / irecv on purpose
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -232,7 +233,7 @@ def main():
     from boundless_b200.feed import bind_to_gpu_numa_node
     all_cpus = os.sched_getaffinity(0)
     numa = bind_to_gpu_numa_node(local_rank, L)
-    os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
+
     slots = max(1, args.slots)
     srv = get_prover_server(ProverOpts(segment_po2=PO2, segment_widths=WIDTHS, slots=slots, device=local_rank))
 
