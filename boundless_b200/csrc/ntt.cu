@@ -54,6 +54,22 @@ __device__ __forceinline__ uint32_t mul_tw(uint32_t x, const tw_t w) {
     const uint32_t r = x * w.x - q * P;          // in [0, 2p)
     return addmin(r, 0u - P, r);
 }
+// Butterfly adds for the transforms.  ptxas splits plain adds between IADD3 (ALU pipe) and IMAD.IADD (the multiplier pipe, which the
+// twiddle products already load more than the ALU); B200_NTT_ADD_V bit 0 / bit 1 write the add / the subtract as VIADDMNMX, which only
+// the ALU executes (the same device B200_P2_ZALL uses in poseidon2.cuh).  Measured: profiles/ntt_addv_r02.txt.
+#ifndef B200_NTT_ADD_V
+#define B200_NTT_ADD_V 0
+#endif
+__device__ __forceinline__ uint32_t nt_add(uint32_t a, uint32_t b) {
+    const uint32_t s = (B200_NTT_ADD_V & 1) ? addmin(a, b, 0xffffffffu) : a + b;
+    return addmin(s, 0u - P, s);
+}
+__device__ __forceinline__ uint32_t nt_sub(uint32_t a, uint32_t b) {
+    const uint32_t d = (B200_NTT_ADD_V & 2) ? addmin(a, 0u - b, 0xffffffffu) : a - b;       // VIADDMNMX takes -b as an operand modifier
+    return addmin(d, P, d);
+}
+// a - b + p in (0, 2p) for a, b < p: enough for mul_tw, which takes any u32 (one three-input add instead of a reduced subtract)
+__device__ __forceinline__ uint32_t nt_subp(uint32_t a, uint32_t b) { return a - b + P; }
 // v * lo * hi with both factors from the two-table decomposition w^e = lo[e & mask] * hi[e >> h]
 __device__ __forceinline__ uint32_t pow_apply(uint32_t v, const tw_t lo, const tw_t hi) { return mul_tw(mul_tw(v, lo), hi); }
 
@@ -79,12 +95,12 @@ __device__ __forceinline__ void ntt_stage(uint32_t* s, const tw_t* __restrict__ 
                 const tw_t w = tw[twbase + (j & (half - 1)) * q];
                 const uint32_t a = x[j], bb = x[j + half];
                 if (DIF) {
-                    x[j] = fp_add(a, bb);
-                    x[j + half] = mul_tw(fp_sub(a, bb), w);
+                    x[j] = nt_add(a, bb);
+                    x[j + half] = mul_tw(nt_subp(a, bb), w);
                 } else {
                     const uint32_t t = mul_tw(bb, w);
-                    x[j] = fp_add(a, t);
-                    x[j + half] = fp_sub(a, t);
+                    x[j] = nt_add(a, t);
+                    x[j + half] = nt_sub(a, t);
                 }
             }
         }
@@ -260,12 +276,12 @@ __device__ __forceinline__ void ntt_stage_c(uint32_t* s, const tw_t* __restrict_
                 const tw_t w = TWS ? *wp : __ldg(wp);      // TWS: table staged in shared memory by TMA
                 const uint32_t a = x[j], bb = x[j + half];
                 if (DIF) {
-                    x[j] = fp_add(a, bb);
-                    x[j + half] = mul_tw(fp_sub(a, bb), w);
+                    x[j] = nt_add(a, bb);
+                    x[j + half] = mul_tw(nt_subp(a, bb), w);
                 } else {
                     const uint32_t t = mul_tw(bb, w);
-                    x[j] = fp_add(a, t);
-                    x[j + half] = fp_sub(a, t);
+                    x[j] = nt_add(a, t);
+                    x[j + half] = nt_sub(a, t);
                 }
             }
         }
@@ -520,8 +536,8 @@ __device__ __forceinline__ void ntt_stage_io(const tw_t* __restrict__ tw, uint32
                 const tw_t* wp = twp + ((1u << LB) >> (l + 1)) + (j & (half - 1)) * q;
                 const tw_t w = TWS ? *wp : __ldg(wp);
                 const uint32_t a = x[j], bb = x[j + half];
-                if (DIF) { x[j] = fp_add(a, bb); x[j + half] = mul_tw(fp_sub(a, bb), w); }
-                else { const uint32_t t = mul_tw(bb, w); x[j] = fp_add(a, t); x[j + half] = fp_sub(a, t); }
+                if (DIF) { x[j] = nt_add(a, bb); x[j + half] = mul_tw(nt_subp(a, bb), w); }
+                else { const uint32_t t = mul_tw(bb, w); x[j] = nt_add(a, t); x[j + half] = nt_sub(a, t); }
             }
         }
     }
@@ -639,12 +655,12 @@ __device__ __forceinline__ void radix32_levels(uint32_t (&x)[32], const tw_t* __
                 if (CONST) w = w32_pair<DIF>(i << (5 - m)); else w = tws[(16u << m) + t + 32u * i];
                 const uint32_t a = x[j], b = x[j + half];
                 if (DIF) {
-                    x[j] = fp_add(a, b);
-                    x[j + half] = one ? fp_sub(a, b) : mul_tw(a - b + P, w);     // a - b + p in (0, 2p): mul_tw takes any u32
+                    x[j] = nt_add(a, b);
+                    x[j + half] = one ? nt_sub(a, b) : mul_tw(nt_subp(a, b), w);     // a - b + p in (0, 2p): mul_tw takes any u32
                 } else {
                     const uint32_t tt = one ? b : mul_tw(b, w);
-                    x[j] = fp_add(a, tt);
-                    x[j + half] = fp_sub(a, tt);
+                    x[j] = nt_add(a, tt);
+                    x[j + half] = nt_sub(a, tt);
                 }
             }
         }
@@ -652,7 +668,8 @@ __device__ __forceinline__ void radix32_levels(uint32_t (&x)[32], const tw_t* __
 }
 
 // LGRS >= 0: row_stride == 2^LGRS is a compile-time constant, so every global address of a tile is base + immediate.
-template <bool DIF, int MINB, int LGRS>
+// POW: the inverse inter-pass twiddle in the epilogue (only when pass B is not the fused kernel that applies it on load).
+template <bool DIF, int MINB, int LGRS, bool POW>
 __global__ void __launch_bounds__(256, MINB) k_ntt_strided_r32(uint32_t* __restrict__ data, uint32_t row_stride_rt, uint32_t tiles_per_poly,
                                                                 uint32_t num_tiles, size_t poly_stride, const tw_t* __restrict__ tw_g,
                                                                 const tw_t* __restrict__ pow_g, uint32_t lg_m) {
@@ -723,7 +740,7 @@ __global__ void __launch_bounds__(256, MINB) k_ntt_strided_r32(uint32_t* __restr
             // exponent col * bitrev10(32 grp + j) = col * bitrev5(grp) + (col << 5) * bitrev5(j): two per-tile values and an immediate
             const uint32_t col = (tile % tiles_per_poly) * 8 + c;
             const uint32_t ea = col * bitrev(grp, 5), eb = col << 5;
-            if (pow_g) {
+            if constexpr (POW) {
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
                     constexpr uint32_t BR5[32] = {0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30,
@@ -738,6 +755,61 @@ __global__ void __launch_bounds__(256, MINB) k_ntt_strided_r32(uint32_t* __restr
         }
         __syncthreads();       // every thread is done with buf before the next iteration's prefetch overwrites it
         cur ^= 1;
+    }
+}
+
+// The same two radix-32 stages with the tile loaded straight into registers (no cp.async staging, no double buffer): the only shared
+// memory is the exchange buffer between the stages (33 KB) and the stage table, so 4 CTAs fit an SM (against 3 with the staged tile)
+// and the loads of one CTA are hidden by the arithmetic of the other three.  A warp's 32-bit accesses cover 4 rows x 32 bytes.
+template <bool DIF, int LGRS>
+__global__ void __launch_bounds__(256, 4) k_ntt_strided_r32d(uint32_t* __restrict__ data, uint32_t row_stride_rt, uint32_t tiles_per_poly,
+                                                             uint32_t num_tiles, size_t poly_stride, const tw_t* __restrict__ tw_g) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    constexpr uint32_t L = 1024, TILE = (L + (L >> 5)) * 8;
+    const uint32_t tid = threadIdx.x;
+    const size_t row_stride = LGRS >= 0 ? ((size_t)1 << (LGRS >= 0 ? LGRS : 0)) : (size_t)row_stride_rt;
+    tw_t* tw_s = reinterpret_cast<tw_t*>(smem + TILE);
+    __shared__ __align__(8) uint64_t tw_bar;
+    if (tid == 0) mbar_init(&tw_bar, 1);
+    __syncthreads();
+    if (tid == 0) tma_load_1d(tw_s, tw_g, L * 8, &tw_bar);
+    const uint32_t c = tid & 7u, grp = tid >> 3;
+    uint32_t* p1 = smem + (33u * grp) * 8u + c;        // rows 32 grp + j
+    uint32_t* p2 = smem + grp * 8u + c;                // rows grp + 32 k
+    bool first = true;
+    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        uint32_t* g0 = data + (size_t)(tile / tiles_per_poly) * poly_stride + (size_t)(tile % tiles_per_poly) * 8 + c;
+        uint32_t* gc = g0 + (size_t)(32u * grp) * row_stride;
+        uint32_t* gs = g0 + (size_t)grp * row_stride;
+        uint32_t x[32];
+        if constexpr (!DIF) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) x[j] = gc[(size_t)j * row_stride];
+            radix32_levels<false, true>(x, nullptr, 0u);
+#pragma unroll
+            for (int j = 0; j < 32; j++) p1[j * 8] = x[j];
+            if (first) { mbar_wait(&tw_bar, 0); first = false; }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 32; k++) x[k] = p2[k * 33 * 8];
+            radix32_levels<false, false>(x, tw_s, grp);
+#pragma unroll
+            for (int k = 0; k < 32; k++) gs[(size_t)(32 * k) * row_stride] = x[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 32; k++) x[k] = gs[(size_t)(32 * k) * row_stride];
+            if (first) { mbar_wait(&tw_bar, 0); first = false; }
+            radix32_levels<true, false>(x, tw_s, grp);
+#pragma unroll
+            for (int k = 0; k < 32; k++) p2[k * 33 * 8] = x[k];
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 32; j++) x[j] = p1[j * 8];
+            radix32_levels<true, true>(x, nullptr, 0u);
+#pragma unroll
+            for (int j = 0; j < 32; j++) gc[(size_t)j * row_stride] = x[j];
+        }
+        __syncthreads();       // the exchange buffer is free again
     }
 }
 
@@ -782,22 +854,22 @@ __global__ void __launch_bounds__(256) k_ntt_fwd1(uint32_t* out, const uint32_t*
             uint32_t y[16];
             {   // level 3 on (c.x, c.y) -> y[0..7], on (c.z, c.w) -> y[8..15]
                 const uint32_t b1 = mul_tw(c.y, w8_1), b2 = mul_tw(c.y, w8_2), b3 = mul_tw(c.y, w8_3);
-                y[0] = fp_add(c.x, c.y); y[4] = fp_sub(c.x, c.y);
-                y[1] = fp_add(c.x, b1);  y[5] = fp_sub(c.x, b1);
-                y[2] = fp_add(c.x, b2);  y[6] = fp_sub(c.x, b2);
-                y[3] = fp_add(c.x, b3);  y[7] = fp_sub(c.x, b3);
+                y[0] = nt_add(c.x, c.y); y[4] = nt_sub(c.x, c.y);
+                y[1] = nt_add(c.x, b1);  y[5] = nt_sub(c.x, b1);
+                y[2] = nt_add(c.x, b2);  y[6] = nt_sub(c.x, b2);
+                y[3] = nt_add(c.x, b3);  y[7] = nt_sub(c.x, b3);
                 const uint32_t d1 = mul_tw(c.w, w8_1), d2 = mul_tw(c.w, w8_2), d3 = mul_tw(c.w, w8_3);
-                y[8] = fp_add(c.z, c.w);  y[12] = fp_sub(c.z, c.w);
-                y[9] = fp_add(c.z, d1);   y[13] = fp_sub(c.z, d1);
-                y[10] = fp_add(c.z, d2);  y[14] = fp_sub(c.z, d2);
-                y[11] = fp_add(c.z, d3);  y[15] = fp_sub(c.z, d3);
+                y[8] = nt_add(c.z, c.w);  y[12] = nt_sub(c.z, c.w);
+                y[9] = nt_add(c.z, d1);   y[13] = nt_sub(c.z, d1);
+                y[10] = nt_add(c.z, d2);  y[14] = nt_sub(c.z, d2);
+                y[11] = nt_add(c.z, d3);  y[15] = nt_sub(c.z, d3);
             }
             uint32_t* dst = tile + rr * rowpad + 17 * t;        // phys(16t + j) = 16t + j + t
 #pragma unroll
             for (int i = 0; i < 8; i++) {                        // level 4
                 const uint32_t bb = i == 0 ? y[8] : mul_tw(y[8 + i], w16[i]);
-                dst[i] = fp_add(y[i], bb);
-                dst[8 + i] = fp_sub(y[i], bb);
+                dst[i] = nt_add(y[i], bb);
+                dst[8 + i] = nt_sub(y[i], bb);
             }
         }
     }
@@ -841,10 +913,14 @@ __global__ void __launch_bounds__(256) k_ntt_fwd1(uint32_t* out, const uint32_t*
 }
 
 // inverse pass B: contiguous rows of Lc values, DIF levels LOGLC..1, in place (out == in allowed), optional scale.
+// pow_g != nullptr: the six-step inter-pass twiddle w_N^-(pos * bitrev(row)) (times the 1/N folded into its table) is applied HERE, to
+// the values as they are loaded, instead of in the epilogue of the strided pass A: there it costs the radix-32 kernel 64 table loads in
+// flight per thread (125 registers, 2 CTAs per SM); here it is 2 multiplies on the way into a kernel that runs at 70 % pipe use.
 template <int LOGLC>
 __global__ void __launch_bounds__(256) k_ntt_invb(uint32_t* out, const uint32_t* in, uint32_t rows_per_cta, uint32_t lg_rpp, uint32_t total_rows,
                                                   size_t in_poly_stride, size_t out_poly_stride, const tw_t* __restrict__ tw_g,
-                                                  uint32_t scale, const tw_t* __restrict__ p3lo, const tw_t* __restrict__ p3hi) {
+                                                  uint32_t scale, const tw_t* __restrict__ p3lo, const tw_t* __restrict__ p3hi,
+                                                  const tw_t* __restrict__ pow_g, uint32_t lg_m) {
     extern __shared__ uint32_t smem[];
     constexpr uint32_t Lc = 1u << LOGLC, rowpad = Lc + (Lc >> 4);
     constexpr int REM = LOGLC - 4;                   // levels after the first radix-16 stage
@@ -856,12 +932,22 @@ __global__ void __launch_bounds__(256) k_ntt_invb(uint32_t* out, const uint32_t*
     const uint32_t row0 = blockIdx.x * rows_per_cta, rpp_mask = (1u << lg_rpp) - 1;
     uint32_t nrows = total_rows - row0; if (nrows > rows_per_cta) nrows = rows_per_cta;
     // ---- first stage: global -> registers -> shared ----
+    const uint32_t hh = (lg_m + 1) / 2, lmask = (1u << hh) - 1, mmask = (1u << lg_m) - 1;
+    const tw_t* plo = pow_g; const tw_t* phi = pow_g + (1u << hh);
     for (uint32_t w = tid; w < nrows << (LOGLC - 4); w += nth) {
         const uint32_t rr = w >> (LOGLC - 4), R = row0 + rr;
         const uint32_t* irow = in + (size_t)(R >> lg_rpp) * in_poly_stride + (size_t)(R & rpp_mask) * Lc;
         uint32_t* trow = tile + rr * rowpad;
+        const uint32_t d1 = pow_g ? bitrev(R & rpp_mask, lg_rpp) : 0u;
         ntt_stage_io<4, LOGLC, true>(tw_g, w & ((1u << (LOGLC - 4)) - 1),
-            [&](uint32_t b0, uint32_t d) { return irow[b0 + d]; },
+            [&](uint32_t b0, uint32_t d) {
+                uint32_t v = irow[b0 + d];
+                if (pow_g) {
+                    const uint32_t e = ((b0 + d) * d1) & mmask;
+                    v = pow_apply(v, __ldg(plo + (e & lmask)), __ldg(phi + (e >> hh)));
+                }
+                return v;
+            },
             [&](uint32_t base, const uint32_t (&x)[16]) {
                 constexpr uint32_t q = Lc >> 4;
 #pragma unroll
@@ -984,10 +1070,24 @@ static cudaError_t run_strided(const DeviceTables* T, uint32_t* d, uint32_t logL
         if (logL == 10 && env_int("B200_NTT_R32", 1)) {
             // radix-32 register kernel: 256 threads, 2 x 1056 x 8 words of tile + the 1024-entry stage table
             const size_t sm32 = (size_t)2 * (1024 + 32) * 8 * 4 + 1024 * 8;
-            const int nb = env_int("B200_NTT_R32_MINB", DIF ? 2 : 3) == 3 ? 3 : 2;      // measured best per direction (tools/time_ntt2.py)
+            // B200_NTT_R32_DIRECT: bit 0 = inverse (DIF) pass, bit 1 = forward (DIT) pass
+            if (!(DIF && pow_g != nullptr) && (env_int("B200_NTT_R32_DIRECT", 3) & (DIF ? 1 : 2))) {
+                const size_t smd = (size_t)(1024 + 32) * 8 * 4 + 1024 * 8;
+                uint32_t gd = (uint32_t)T->sm_count * 4u; if (gd > num_tiles) gd = num_tiles;
+                const int lg = row_stride == 1024 ? 10 : (row_stride == 4096 ? 12 : -1);
+#define B200_R32D_LAUNCH(RS) { auto kp = k_ntt_strided_r32d<DIF, RS>; \
+                    cudaError_t e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smd); if (e != cudaSuccess) return e; \
+                    B200_LAUNCH(kp)<<<gd, 256, smd, s>>>(d, row_stride, tpp, num_tiles, poly_stride, twt); return cudaGetLastError(); }
+                if (lg == 10) B200_R32D_LAUNCH(10) else if (lg == 12) B200_R32D_LAUNCH(12) else B200_R32D_LAUNCH(-1)
+#undef B200_R32D_LAUNCH
+            }
+            // CTAs per SM: measured best per direction (tools/time_ntt2.py); the inverse pass runs the same at 2 and 3 with or without
+            // the twiddle epilogue (profiles/ntt_tw_in_b_r02.txt)
+            const bool pw = DIF && pow_g != nullptr;
+            const int nb = env_int("B200_NTT_R32_MINB", DIF ? 2 : 3) == 3 ? 3 : 2;
             uint32_t g32 = (uint32_t)T->sm_count * (uint32_t)nb; if (g32 > num_tiles) g32 = num_tiles;
             const int lgrs = row_stride == 1024 ? 10 : (row_stride == 4096 ? 12 : -1);
-#define B200_R32_LAUNCH(NB, RS) { auto kp = k_ntt_strided_r32<DIF, NB, RS>; \
+#define B200_R32_LAUNCH(NB, RS) { auto kp = pw ? k_ntt_strided_r32<DIF, NB, RS, DIF> : k_ntt_strided_r32<DIF, NB, RS, false>; \
                 cudaError_t e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm32); if (e != cudaSuccess) return e; \
                 B200_LAUNCH(kp)<<<g32, 256, sm32, s>>>(d, row_stride, tpp, num_tiles, poly_stride, twt, pow_g, lg_m); return cudaGetLastError(); }
             if (nb == 3) { if (lgrs == 10) B200_R32_LAUNCH(3, 10) else if (lgrs == 12) B200_R32_LAUNCH(3, 12) else B200_R32_LAUNCH(3, -1) }
@@ -1039,8 +1139,7 @@ static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32
         const size_t sm = (size_t)rpc * (Lc + (Lc >> 4)) * 4;
 #define B200_FUSED_CASE(LL) case LL: { cudaError_t e; \
             if (DIF) { auto kf = k_ntt_invb<LL>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
-                if (pow_g) break; \
-                B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, scale, p3lo, p3hi); \
+                B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, scale, p3lo, p3hi, pow_g, lg_m); \
                 if (shift_done) *shift_done = p3lo != nullptr; } \
             else if (lg_e == 2) { auto kf = k_ntt_fwd1<LL, 2>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
                 if (scale) break; \
@@ -1069,6 +1168,12 @@ static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32
     return cudaGetLastError();
 }
 
+// true when pass B of a two-pass inverse transform runs in the fused kernel k_ntt_invb (run_contig<true>'s first branch), which can
+// apply the inter-pass twiddle on load; B200_NTT_TW_IN_B=0 keeps it in pass A's epilogue (round 1's arrangement) for A/B timing
+static bool twiddle_in_pass_b(const uint32_t* d_io, uint32_t n2, size_t N) {
+    return n2 >= 8 && n2 <= 13 && env_int("B200_NTT_FUSED", 1) && env_int("B200_NTT_TW_IN_B", 1) && ((uintptr_t)d_io & 15) == 0 && N % 4 == 0;
+}
+
 cudaError_t launch_batch_intt(const DeviceTables* T, uint32_t* d_io, uint32_t lg_n, uint32_t count, cudaStream_t s) {
     if (lg_n == 0 || count == 0) return cudaSuccess;
     if (lg_n > MAX_LG) return cudaErrorInvalidValue;
@@ -1087,11 +1192,12 @@ cudaError_t launch_batch_intt(const DeviceTables* T, uint32_t* d_io, uint32_t lg
         return launch_batch_intt(T, d_io, n2, count << BIG_N1, s);
     }
     const uint32_t n1 = split_n1(lg_n), n2 = lg_n - n1;
-    // pass A: DIF over i1 (rows of stride N2) + twiddle (1/N folded into the table)
-    cudaError_t e = run_strided<true>(T, d_io, n1, 1u << n2, 1u << n2, count, N, T->pow_inv[lg_n], lg_n, s);
+    const bool tw_b = twiddle_in_pass_b(d_io, n2, N);
+    // pass A: DIF over i1 (rows of stride N2); the inter-pass twiddle (1/N folded into its table) here or on pass B's loads
+    cudaError_t e = run_strided<true>(T, d_io, n1, 1u << n2, 1u << n2, count, N, tw_b ? nullptr : T->pow_inv[lg_n], lg_n, s);
     if (e != cudaSuccess) return e;
     // pass B: DIF over each contiguous row of N2
-    return run_contig<true>(T, d_io, d_io, n2, 0, 1u << n1, count, N, N, nullptr, 0, 0, 0, s);
+    return run_contig<true>(T, d_io, d_io, n2, 0, 1u << n1, count, N, N, tw_b ? T->pow_inv[lg_n] : nullptr, lg_n, 0, 0, s);
 }
 
 // K1 + K2 in one go: iNTT whose last pass multiplies the coefficient of x^d by 3^d (falls back to two launches when the
@@ -1111,9 +1217,10 @@ cudaError_t launch_batch_intt_shift(const DeviceTables* T, uint32_t* d_io, uint3
         e = run_contig<true>(T, d_io, d_io, lg_n, 0, 1, count, N, N, nullptr, 0, 0, scale, s, T->p3lo, T->p3hi, &done);
     } else {
         const uint32_t n1 = split_n1(lg_n), n2 = lg_n - n1;
-        e = run_strided<true>(T, d_io, n1, 1u << n2, 1u << n2, count, N, T->pow_inv[lg_n], lg_n, s);
+        const bool tw_b = twiddle_in_pass_b(d_io, n2, N);
+        e = run_strided<true>(T, d_io, n1, 1u << n2, 1u << n2, count, N, tw_b ? nullptr : T->pow_inv[lg_n], lg_n, s);
         if (e != cudaSuccess) return e;
-        e = run_contig<true>(T, d_io, d_io, n2, 0, 1u << n1, count, N, N, nullptr, 0, 0, 0, s, T->p3lo, T->p3hi, &done);
+        e = run_contig<true>(T, d_io, d_io, n2, 0, 1u << n1, count, N, N, tw_b ? T->pow_inv[lg_n] : nullptr, lg_n, 0, 0, s, T->p3lo, T->p3hi, &done);
     }
     if (e != cudaSuccess) return e;
     return done ? cudaSuccess : launch_zk_shift(T, d_io, lg_n, count, s);
