@@ -39,7 +39,19 @@ struct DeviceTables {
     uint2* p3lo;
     uint2* p3hi;
     uint32_t rou_fwd[28], rou_rev[28];  // host copies, Montgomery
+    // [r2] per-element tables in the DATA layout of a two-pass transform of size 2^m split as 2^full_rows[..][m] rows (get_full_table):
+    // one coalesced 8-byte load and ONE multiply per element instead of two table gathers, an exponent and two multiplies.
+    uint2* full[3][MAX_LG + 1];
+    uint32_t full_rows[3][MAX_LG + 1];
 };
+// kind of a full table: element (rho, pos) of a 2^lg_rows x 2^(lg_m - lg_rows) matrix, index rho * 2^(lg_m - lg_rows) + pos, holds
+//   FULL_INV / FULL_FWD: the inter-pass twiddle pow_inv / pow_fwd [lg_m] ^ (pos * bitrev(rho))      (inverse: normalisation folded in)
+//   FULL_ZK:             3^(bitrev(rho) + 2^lg_rows * bitrev(pos)), the zk_shift factor of that slot of the bit-reversed coefficients
+enum { FULL_INV = 0, FULL_FWD = 1, FULL_ZK = 2 };
+// Built on first use (host-computed, synchronous upload; thread-safe), 8 * 2^lg_m bytes each; nullptr when lg_m exceeds
+// B200_NTT_FULL_MAX_LG (default 22), when B200_NTT_FULL=0, on allocation failure, or when the table of this size exists with another
+// split -- callers then use the two-table decomposition above.
+const uint2* get_full_table(const DeviceTables* T, int kind, uint32_t lg_m, uint32_t lg_rows);
 const DeviceTables* get_tables(int device);   // lazily built, thread-safe; nullptr + error string on failure
 void free_tables();                           // b200_shutdown
 void compat_release();                        // b200_shutdown: scratch arena of the risc0-sys compatible supra_poly_divide (compat.cu)

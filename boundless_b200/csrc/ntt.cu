@@ -819,7 +819,7 @@ template <int LOGLC, int LGE>
 __global__ void __launch_bounds__(256) k_ntt_fwd1(uint32_t* out, const uint32_t* in, uint32_t rows_per_cta, uint32_t lg_rpp,
                                                   uint32_t total_rows, size_t in_poly_stride, size_t out_poly_stride,
                                                   const tw_t* __restrict__ tw_g, const tw_t* __restrict__ pow_g, uint32_t lg_m,
-                                                  uint32_t lg_rows) {
+                                                  uint32_t lg_rows, const tw_t* __restrict__ tw_full) {
     extern __shared__ uint32_t smem[];
     static_assert(LGE == 0 || LGE == 2, "blow-up 1 or 4");
     constexpr uint32_t Lc = 1u << LOGLC, Lin = Lc >> LGE, rowpad = Lc + (Lc >> 4);
@@ -900,6 +900,12 @@ __global__ void __launch_bounds__(256) k_ntt_fwd1(uint32_t* out, const uint32_t*
             [&](uint32_t b0, uint32_t d) { return trow[(b0 + (b0 >> 4)) + (d + (d >> 4))]; },
             [&](uint32_t base, const uint32_t (&x)[16]) {
                 constexpr uint32_t q = Lc >> 4;
+                if (tw_full) {      // inter-pass twiddle from the table in data layout (get_full_table)
+                    const tw_t* tf = tw_full + (size_t)rho * Lc + base;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) orow[base + j * q] = mul_tw(x[j], __ldg(tf + j * q));
+                    return;
+                }
                 uint32_t e = (base * d1) & mmask;
                 const uint32_t estep = (q * d1) & mmask;
 #pragma unroll
@@ -950,7 +956,6 @@ __global__ void __launch_bounds__(256) k_ntt_invb(uint32_t* out, const uint32_t*
             },
             [&](uint32_t base, const uint32_t (&x)[16]) {
                 constexpr uint32_t q = Lc >> 4;
-#pragma unroll
                 const uint32_t pb = base + (base >> 4);
 #pragma unroll
                 for (int j = 0; j < 16; j++) trow[pb + AddrContig::off(j * q)] = x[j];
@@ -990,6 +995,88 @@ __global__ void __launch_bounds__(256) k_ntt_invb(uint32_t* out, const uint32_t*
                     for (int j = 0; j < (1 << KF); j += 4) *reinterpret_cast<uint4*>(orow + base + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
             });
+    }
+}
+
+// inverse pass B for rows of 1024 values (the 2^20 transform of the segment's columns) in the radix-32 register structure: ONE WARP per
+// row.  Lane t loads elements t + 32k (coalesced, with the inter-pass twiddle), runs levels 10..6, the 32 x 32 exchange goes through the
+// warp's own 1056 words of shared memory (element i at i + i/32: both access patterns conflict-free), levels 5..1 run on elements
+// 32t..32t+31 with immediate twiddles, and the result goes back through the same words so that the stores are 16-byte and coalesced.
+// No block barrier anywhere: the warps of a CTA only share the TMA-staged stage table.
+__global__ void __launch_bounds__(256, 3) k_ntt_invb_r32(uint32_t* out, const uint32_t* in, uint32_t lg_rpp, uint32_t total_rows,
+                                                         size_t in_poly_stride, size_t out_poly_stride, const tw_t* __restrict__ tw_g,
+                                                         uint32_t scale, const tw_t* __restrict__ p3lo, const tw_t* __restrict__ p3hi,
+                                                         const tw_t* __restrict__ pow_g, uint32_t lg_m,
+                                                         const tw_t* __restrict__ tw_full, const tw_t* __restrict__ zk_full) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    constexpr uint32_t Lc = 1024, ROWW = Lc + (Lc >> 5);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    tw_t* tw_s = reinterpret_cast<tw_t*>(smem + 8 * ROWW);
+    __shared__ __align__(8) uint64_t tw_bar;
+    if (tid == 0) mbar_init(&tw_bar, 1);
+    __syncthreads();
+    if (tid == 0) tma_load_1d(tw_s, tw_g, Lc * 8, &tw_bar);
+    uint32_t* buf = smem + warp * ROWW;
+    const uint32_t hh = (lg_m + 1) / 2, lmask = (1u << hh) - 1, mmask = (1u << lg_m) - 1, rpp_mask = (1u << lg_rpp) - 1;
+    const tw_t* plo = pow_g; const tw_t* phi = pow_g + (1u << hh);
+    const uint32_t brl = bitrev(lane, 5);
+    bool first = true;
+    for (uint32_t R = blockIdx.x * 8 + warp; R < total_rows; R += gridDim.x * 8) {
+        const uint32_t rho = R & rpp_mask, d1 = bitrev(rho, lg_rpp);
+        const uint32_t* irow = in + (size_t)(R >> lg_rpp) * in_poly_stride + (size_t)rho * Lc + lane;
+        uint32_t x[32];
+#pragma unroll
+        for (int k = 0; k < 32; k++) x[k] = irow[32 * k];
+        if (tw_full) {        // inter-pass twiddle from the table in data layout (get_full_table): one coalesced load, one multiply
+            const tw_t* tf = tw_full + (size_t)rho * Lc + lane;
+#pragma unroll
+            for (int k = 0; k < 32; k++) x[k] = mul_tw(x[k], __ldg(tf + 32 * k));
+        } else if (pow_g) {
+            uint32_t e = (lane * d1) & mmask;
+            const uint32_t estep = (32u * d1) & mmask;
+#pragma unroll
+            for (int k = 0; k < 32; k++) { x[k] = pow_apply(x[k], __ldg(plo + (e & lmask)), __ldg(phi + (e >> hh))); e = (e + estep) & mmask; }
+        }
+        if (first) { mbar_wait(&tw_bar, 0); first = false; }
+        radix32_levels<true, false>(x, tw_s, lane);
+#pragma unroll
+        for (int k = 0; k < 32; k++) buf[lane + 33 * k] = x[k];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; j++) x[j] = buf[33 * lane + j];
+        radix32_levels<true, true>(x, nullptr, 0u);
+        if (scale) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) x[j] = fp_mul(x[j], scale);
+        }
+        if (p3lo && !zk_full) {   // fused zk_shift: slot 32 t + j holds degree bitrev(row) + rows_per_poly * bitrev10(32 t + j); multiply by 3^d
+            constexpr uint32_t BR5[32] = {0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30,
+                                          1, 17, 9, 25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31};
+            const uint32_t da = d1 + (brl << lg_rpp);
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const uint32_t d = da + ((BR5[j] << 5) << lg_rpp);
+                x[j] = pow_apply(x[j], __ldg(p3lo + (d & 4095)), __ldg(p3hi + (d >> 12)));
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; j++) buf[33 * lane + j] = x[j];
+        __syncwarp();
+        uint32_t* orow = out + (size_t)(R >> lg_rpp) * out_poly_stride + (size_t)rho * Lc;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t idx = i * 128 + lane * 4, pa = idx + (idx >> 5);
+            uint4 v = make_uint4(buf[pa], buf[pa + 1], buf[pa + 2], buf[pa + 3]);
+            if (p3lo && zk_full) {      // fused zk_shift from the table in data layout: four factors = two 16-byte loads
+                const uint4* zf = reinterpret_cast<const uint4*>(zk_full + (size_t)rho * Lc + idx);
+                const uint4 z0 = __ldg(zf), z1 = __ldg(zf + 1);
+                v.x = mul_tw(v.x, make_uint2(z0.x, z0.y)); v.y = mul_tw(v.y, make_uint2(z0.z, z0.w));
+                v.z = mul_tw(v.z, make_uint2(z1.x, z1.y)); v.w = mul_tw(v.w, make_uint2(z1.z, z1.w));
+            }
+            *reinterpret_cast<uint4*>(orow + idx) = v;
+        }
+        __syncwarp();
     }
 }
 
@@ -1125,6 +1212,8 @@ static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32
                               uint32_t count, size_t in_stride, size_t out_stride, const tw_t* pow_g, uint32_t lg_m,
                               uint32_t lg_rows, uint32_t scale, cudaStream_t s, const tw_t* p3lo = nullptr, const tw_t* p3hi = nullptr,
                               bool* shift_done = nullptr) {
+    // per-element tables in data layout for the kernels that can use them (nullptr: the two-table decomposition)
+    const tw_t* tw_full = nullptr; const tw_t* zk_full = nullptr;
     uint32_t rpc = logLc >= 12 ? 1 : (1u << (12 - logLc));
     const uint64_t total_rows = (uint64_t)rows_per_poly * count;
     if (rpc > total_rows) rpc = (uint32_t)total_rows;
@@ -1137,16 +1226,30 @@ static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32
     if (logLc >= 8 && logLc <= 13 && (DIF ? lg_e == 0 : (lg_e == 2 || lg_e == 0)) && (1u << lg_rpp) == rows_per_poly && env_int("B200_NTT_FUSED", 1) &&
         (((uintptr_t)in | (uintptr_t)out) & 15) == 0 && in_stride % 4 == 0 && out_stride % 4 == 0) {
         const size_t sm = (size_t)rpc * (Lc + (Lc >> 4)) * 4;
+        if (DIF && logLc == 10 && env_int("B200_NTT_INVB_R32", 1)) {
+            if (pow_g && lg_m == logLc + lg_rpp) tw_full = get_full_table(T, FULL_INV, lg_m, lg_rpp);
+            if (p3lo) zk_full = get_full_table(T, FULL_ZK, logLc + lg_rpp, lg_rpp);
+            const size_t smr = (size_t)8 * (1024 + 32) * 4 + 1024 * 8;
+            cudaError_t e = cudaFuncSetAttribute(k_ntt_invb_r32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); if (e != cudaSuccess) return e;
+            // one CTA per 8 rows by default; B200_NTT_INVB_R32_WAVES = w > 0 caps the grid at w resident waves (persistent loop)
+            uint32_t gr = (uint32_t)((total_rows + 7) / 8);
+            const uint32_t waves = (uint32_t)env_int("B200_NTT_INVB_R32_WAVES", 0), gmax = (uint32_t)T->sm_count * 3u * waves;
+            if (waves && gr > gmax) gr = gmax;
+            B200_LAUNCH(k_ntt_invb_r32)<<<gr, 256, smr, s>>>(out, in, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, scale, p3lo, p3hi, pow_g, lg_m, tw_full, zk_full);
+            if (shift_done) *shift_done = p3lo != nullptr;
+            return cudaGetLastError();
+        }
+        if (!DIF && pow_g && lg_m == logLc + lg_rpp && lg_rows == lg_rpp) tw_full = get_full_table(T, FULL_FWD, lg_m, lg_rpp);
 #define B200_FUSED_CASE(LL) case LL: { cudaError_t e; \
             if (DIF) { auto kf = k_ntt_invb<LL>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
                 B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, scale, p3lo, p3hi, pow_g, lg_m); \
                 if (shift_done) *shift_done = p3lo != nullptr; } \
             else if (lg_e == 2) { auto kf = k_ntt_fwd1<LL, 2>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
                 if (scale) break; \
-                B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, pow_g, lg_m, lg_rows); } \
+                B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, pow_g, lg_m, lg_rows, tw_full); } \
             else { auto kf = k_ntt_fwd1<LL, 0>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
                 if (scale) break; \
-                B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, pow_g, lg_m, lg_rows); } \
+                B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, pow_g, lg_m, lg_rows, tw_full); } \
             return cudaGetLastError(); }
         switch (logLc) { B200_FUSED_CASE(8) B200_FUSED_CASE(9) B200_FUSED_CASE(10) B200_FUSED_CASE(11) B200_FUSED_CASE(12) B200_FUSED_CASE(13) default: break; }
 #undef B200_FUSED_CASE
