@@ -761,8 +761,8 @@ __global__ void __launch_bounds__(256, MINB) k_ntt_strided_r32(uint32_t* __restr
 // The same two radix-32 stages with the tile loaded straight into registers (no cp.async staging, no double buffer): the only shared
 // memory is the exchange buffer between the stages (33 KB) and the stage table, so 4 CTAs fit an SM (against 3 with the staged tile)
 // and the loads of one CTA are hidden by the arithmetic of the other three.  A warp's 32-bit accesses cover 4 rows x 32 bytes.
-template <bool DIF, int LGRS>
-__global__ void __launch_bounds__(256, 4) k_ntt_strided_r32d(uint32_t* __restrict__ data, uint32_t row_stride_rt, uint32_t tiles_per_poly,
+template <bool DIF, int LGRS, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_ntt_strided_r32d(uint32_t* __restrict__ data, uint32_t row_stride_rt, uint32_t tiles_per_poly,
                                                              uint32_t num_tiles, size_t poly_stride, const tw_t* __restrict__ tw_g) {
     extern __shared__ __align__(16) uint32_t smem[];
     constexpr uint32_t L = 1024, TILE = (L + (L >> 5)) * 8;
@@ -815,8 +815,10 @@ __global__ void __launch_bounds__(256, 4) k_ntt_strided_r32d(uint32_t* __restric
 
 // forward pass 1: rows of Lin = Lc/4 bit-reversed coefficients -> Lc values (levels 3..LOGLC of the size-Lc DIT), times
 // w_M^(k * d1).  One work item of the head = 4 coefficients -> 16 consecutive positions (levels 3 and 4 in registers).
-template <int LOGLC, int LGE>
-__global__ void __launch_bounds__(256) k_ntt_fwd1(uint32_t* out, const uint32_t* in, uint32_t rows_per_cta, uint32_t lg_rpp,
+// MINB: CTAs per SM the register allocation aims at.  The expanding form fits 40 registers (6 CTAs) without spills and is 6 % faster
+// there than at its natural 48 (profiles/ntt_fwd1_minb_r02.txt); the plain form needs 59 (4 CTAs).
+template <int LOGLC, int LGE, int MINB = (LGE == 2 ? 6 : 4)>
+__global__ void __launch_bounds__(256, MINB) k_ntt_fwd1(uint32_t* out, const uint32_t* in, uint32_t rows_per_cta, uint32_t lg_rpp,
                                                   uint32_t total_rows, size_t in_poly_stride, size_t out_poly_stride,
                                                   const tw_t* __restrict__ tw_g, const tw_t* __restrict__ pow_g, uint32_t lg_m,
                                                   uint32_t lg_rows, const tw_t* __restrict__ tw_full) {
@@ -1003,7 +1005,8 @@ __global__ void __launch_bounds__(256) k_ntt_invb(uint32_t* out, const uint32_t*
 // warp's own 1056 words of shared memory (element i at i + i/32: both access patterns conflict-free), levels 5..1 run on elements
 // 32t..32t+31 with immediate twiddles, and the result goes back through the same words so that the stores are 16-byte and coalesced.
 // No block barrier anywhere: the warps of a CTA only share the TMA-staged stage table.
-__global__ void __launch_bounds__(256, 3) k_ntt_invb_r32(uint32_t* out, const uint32_t* in, uint32_t lg_rpp, uint32_t total_rows,
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_ntt_invb_r32(uint32_t* out, const uint32_t* in, uint32_t lg_rpp, uint32_t total_rows,
                                                          size_t in_poly_stride, size_t out_poly_stride, const tw_t* __restrict__ tw_g,
                                                          uint32_t scale, const tw_t* __restrict__ p3lo, const tw_t* __restrict__ p3hi,
                                                          const tw_t* __restrict__ pow_g, uint32_t lg_m,
@@ -1160,12 +1163,16 @@ static cudaError_t run_strided(const DeviceTables* T, uint32_t* d, uint32_t logL
             // B200_NTT_R32_DIRECT: bit 0 = inverse (DIF) pass, bit 1 = forward (DIT) pass
             if (!(DIF && pow_g != nullptr) && (env_int("B200_NTT_R32_DIRECT", 3) & (DIF ? 1 : 2))) {
                 const size_t smd = (size_t)(1024 + 32) * 8 * 4 + 1024 * 8;
-                uint32_t gd = (uint32_t)T->sm_count * 4u; if (gd > num_tiles) gd = num_tiles;
+                const int mb = env_int("B200_NTT_R32D_MINB", 4) == 5 ? 5 : 4;     // CTAs per SM (60 / 48 registers); 5 measured 12 % slower (profiles/ntt_minb_r02.txt)
+                uint32_t gd = (uint32_t)T->sm_count * (uint32_t)mb; if (gd > num_tiles) gd = num_tiles;
                 const int lg = row_stride == 1024 ? 10 : (row_stride == 4096 ? 12 : -1);
-#define B200_R32D_LAUNCH(RS) { auto kp = k_ntt_strided_r32d<DIF, RS>; \
+#define B200_R32D_LAUNCH(RS) { auto kp = mb == 5 ? k_ntt_strided_r32d<DIF, RS, 5> : k_ntt_strided_r32d<DIF, RS, 4>; \
                     cudaError_t e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smd); if (e != cudaSuccess) return e; \
                     B200_LAUNCH(kp)<<<gd, 256, smd, s>>>(d, row_stride, tpp, num_tiles, poly_stride, twt); return cudaGetLastError(); }
-                if (lg == 10) B200_R32D_LAUNCH(10) else if (lg == 12) B200_R32D_LAUNCH(12) else B200_R32D_LAUNCH(-1)
+                if (lg == 10) B200_R32D_LAUNCH(10) else if (lg == 12) B200_R32D_LAUNCH(12)
+                else { auto kp = k_ntt_strided_r32d<DIF, -1, 4>; gd = (uint32_t)T->sm_count * 4u; if (gd > num_tiles) gd = num_tiles;
+                    cudaError_t e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smd); if (e != cudaSuccess) return e;
+                    B200_LAUNCH(kp)<<<gd, 256, smd, s>>>(d, row_stride, tpp, num_tiles, poly_stride, twt); return cudaGetLastError(); }
 #undef B200_R32D_LAUNCH
             }
             // CTAs per SM: measured best per direction (tools/time_ntt2.py); the inverse pass runs the same at 2 and 3 with or without
@@ -1230,12 +1237,14 @@ static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32
             if (pow_g && lg_m == logLc + lg_rpp) tw_full = get_full_table(T, FULL_INV, lg_m, lg_rpp);
             if (p3lo) zk_full = get_full_table(T, FULL_ZK, logLc + lg_rpp, lg_rpp);
             const size_t smr = (size_t)8 * (1024 + 32) * 4 + 1024 * 8;
-            cudaError_t e = cudaFuncSetAttribute(k_ntt_invb_r32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); if (e != cudaSuccess) return e;
+            const int mb = env_int("B200_NTT_INVB_R32_MINB", 3) == 4 ? 4 : 3;     // CTAs per SM (80 / 64 registers): no measurable difference
+            auto kr = mb == 4 ? k_ntt_invb_r32<4> : k_ntt_invb_r32<3>;
+            cudaError_t e = cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); if (e != cudaSuccess) return e;
             // one CTA per 8 rows by default; B200_NTT_INVB_R32_WAVES = w > 0 caps the grid at w resident waves (persistent loop)
             uint32_t gr = (uint32_t)((total_rows + 7) / 8);
-            const uint32_t waves = (uint32_t)env_int("B200_NTT_INVB_R32_WAVES", 0), gmax = (uint32_t)T->sm_count * 3u * waves;
+            const uint32_t waves = (uint32_t)env_int("B200_NTT_INVB_R32_WAVES", 0), gmax = (uint32_t)T->sm_count * (uint32_t)mb * waves;
             if (waves && gr > gmax) gr = gmax;
-            B200_LAUNCH(k_ntt_invb_r32)<<<gr, 256, smr, s>>>(out, in, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, scale, p3lo, p3hi, pow_g, lg_m, tw_full, zk_full);
+            B200_LAUNCH(kr)<<<gr, 256, smr, s>>>(out, in, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, scale, p3lo, p3hi, pow_g, lg_m, tw_full, zk_full);
             if (shift_done) *shift_done = p3lo != nullptr;
             return cudaGetLastError();
         }
@@ -1244,7 +1253,7 @@ static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32
             if (DIF) { auto kf = k_ntt_invb<LL>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
                 B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, scale, p3lo, p3hi, pow_g, lg_m); \
                 if (shift_done) *shift_done = p3lo != nullptr; } \
-            else if (lg_e == 2) { auto kf = k_ntt_fwd1<LL, 2>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
+            else if (lg_e == 2) { auto kf = env_int("B200_NTT_FWD1_MINB", 6) == 5 ? k_ntt_fwd1<LL, 2, 5> : k_ntt_fwd1<LL, 2>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
                 if (scale) break; \
                 B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, pow_g, lg_m, lg_rows, tw_full); } \
             else { auto kf = k_ntt_fwd1<LL, 0>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \

@@ -14,6 +14,11 @@ want = [("time_us", "gpu__time_duration.sum"), ("inst_M", "smsp__inst_executed.s
         ("st_bar", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"),
         ("st_mio", "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio"),
         ("st_lg", "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio"),
+        ("st_wait", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"),
+        ("st_nosel", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"),
+        ("st_noinst", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio"),
+        ("st_disp", "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio"),
+        ("l2hit%", "lts__t_sector_hit_rate.pct"),
         ("bankconf_M", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"), ("smem_wf_M", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")]
 print("%-34s" % "kernel" + "".join("%10s" % w[0] for w in want))
 seen = {}

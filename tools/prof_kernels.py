@@ -22,6 +22,13 @@ if "ntt" in what:
         assert L.b200_batch_zk_shift(p(a), n, cnt, None) is None
         assert L.b200_batch_expand_ntt(p(o), p(a), n, 2, cnt, None) is None
     torch.cuda.synchronize()
+if "ntt2" in what:     # round 2 final arrangement: fused iNTT + zk_shift (2 kernels), expand + NTT (2 kernels)
+    a = torch.randint(0, P, (cnt << n,), dtype=torch.int32, device="cuda")
+    o = torch.empty(cnt << (n + 2), dtype=torch.int32, device="cuda")
+    for _ in range(3):
+        assert L.b200_batch_intt_zk_shift(p(a), n, cnt, None) is None
+        assert L.b200_batch_expand_ntt(p(o), p(a), n, 2, cnt, None) is None
+    torch.cuda.synchronize()
 if "rows" in what:
     rows, cols = 1 << 22, 32
     m = torch.randint(0, P, (rows * cols,), dtype=torch.int32, device="cuda")
