@@ -327,6 +327,9 @@ static __device__ const uint32_t g_diag_w[24] = B200_P2_DIAG_INIT;
 #ifndef B200_P2W_REDUX
 #define B200_P2W_REDUX 1
 #endif
+#ifndef B200_P2W_LAT
+#define B200_P2W_LAT 1      // 1: the latency form of P2Warp below (round 2); 0: the first form (kept for A/B builds)
+#endif
 struct P2Warp {
     uint32_t lane, m4[4], diag;       // this lane's M4 row (Montgomery form of the small integers) and diagonal entry
     uint32_t rc[8];                   // this lane's round constant of each full round
@@ -341,6 +344,7 @@ struct P2Warp {
 #pragma unroll
         for (int k = 0; k < 8; k++) rc[k] = lane < 24 ? g_rc_w[(k < 4 ? 24 * k : 117 + 24 * (k - 4)) + lane] : 0u;
     }
+#if B200_P2W_LAT == 0
     __device__ __forceinline__ uint32_t m_ext(uint32_t x) const {
         const uint32_t q = lane & ~3u;
         const uint32_t x0 = __shfl_sync(0xffffffffu, x, q), x1 = __shfl_sync(0xffffffffu, x, q + 1);
@@ -381,6 +385,50 @@ struct P2Warp {
         for (int r = 4; r < 8; r++) x = m_ext(p2_sbox(fp_add(x, rc[r])));
         return x;
     }
+#else
+    // Latency form (round 2): one permutation per warp is a dependent chain, so what counts is its length, not the instruction count.
+    //  * external layer: the column sum over the six quads is five INDEPENDENT shuffles and a three-level add tree instead of three
+    //    dependent shuffle + add steps;
+    //  * internal round: new x_i = diag_i x_i + (sum of cells 1..23) + sbox(x_0).  diag_i x_i (lanes 1..23) and the REDUX sum run beside
+    //    the S-box; lane 0 never waits for a shuffle, it takes (diag_0 + 1) sbox(x_0) + sum from its own registers; the other lanes add
+    //    the broadcast S-box output last.  The next round constant is fetched a round ahead.
+    __device__ __forceinline__ uint32_t m_ext(uint32_t x) const {
+        const uint32_t q = lane & ~3u;
+        const uint32_t x0 = __shfl_sync(0xffffffffu, x, q), x1 = __shfl_sync(0xffffffffu, x, q + 1);
+        const uint32_t x2 = __shfl_sync(0xffffffffu, x, q + 2), x3 = __shfl_sync(0xffffffffu, x, q + 3);
+        const uint32_t y = fp_add(fp_add(fp_mul(m4[0], x0), fp_mul(m4[1], x1)), fp_add(fp_mul(m4[2], x2), fp_mul(m4[3], x3)));
+        // lanes 24..31 hold y = 0 (their x is 0), so a rotation by 4k over all 32 lanes visits the six quads and two zero quads
+        const uint32_t y1 = __shfl_sync(0xffffffffu, y, lane + 4), y2 = __shfl_sync(0xffffffffu, y, lane + 8);
+        const uint32_t y3 = __shfl_sync(0xffffffffu, y, lane + 12), y4 = __shfl_sync(0xffffffffu, y, lane + 16);
+        const uint32_t y5 = __shfl_sync(0xffffffffu, y, lane + 20), y6 = __shfl_sync(0xffffffffu, y, lane + 24);
+        const uint32_t y7 = __shfl_sync(0xffffffffu, y, lane + 28);
+        const uint32_t s = fp_add(fp_add(fp_add(y, y), fp_add(y1, y2)), fp_add(fp_add(y3, y4), fp_add(fp_add(y5, y6), y7)));
+        return lane < 24 ? s : 0u;
+    }
+    __device__ __forceinline__ uint32_t permute(uint32_t x) const {
+        x = m_ext(x);
+#pragma unroll
+        for (int r = 0; r < 4; r++) x = m_ext(p2_sbox(fp_add(x, rc[r])));      // lanes >= 24: sbox(0) = 0
+        const uint32_t dplus0 = fp_add(__shfl_sync(0xffffffffu, diag, 0), R1);    // diag_0 + 1 (Montgomery one)
+        uint32_t rcr = c_rc[96];
+#pragma unroll 1
+        for (int r = 0; r < 21; r++) {
+            const uint32_t rcn = c_rc[96 + (r < 20 ? r + 1 : r)];
+            const uint32_t c0 = p2_sbox(fp_add(x, rcr));                           // lane 0's is the round's S-box output
+            const uint32_t s = lane == 0 ? 0u : x;
+            const uint32_t lo = __reduce_add_sync(0xffffffffu, s & 0xffffu), hi = __reduce_add_sync(0xffffffffu, s >> 16);
+            const uint32_t srest = fp_reduce38(((uint64_t)hi << 16) + lo);         // cells 1..23, same value in every lane
+            const uint32_t t = fp_add(fp_mul(diag, x), srest);                     // lanes 1..23: everything but the S-box output
+            const uint32_t m0 = fp_add(fp_mul(dplus0, c0), srest);                 // lane 0: complete
+            const uint32_t c0b = __shfl_sync(0xffffffffu, c0, 0);
+            x = lane == 0 ? m0 : (lane < 24 ? fp_add(t, c0b) : 0u);
+            rcr = rcn;
+        }
+#pragma unroll
+        for (int r = 4; r < 8; r++) x = m_ext(p2_sbox(fp_add(x, rc[r])));
+        return x;
+    }
+#endif
 };
 
 #endif  // B200_HOST_EMULATION
