@@ -928,7 +928,8 @@ template <int LOGLC>
 __global__ void __launch_bounds__(256) k_ntt_invb(uint32_t* out, const uint32_t* in, uint32_t rows_per_cta, uint32_t lg_rpp, uint32_t total_rows,
                                                   size_t in_poly_stride, size_t out_poly_stride, const tw_t* __restrict__ tw_g,
                                                   uint32_t scale, const tw_t* __restrict__ p3lo, const tw_t* __restrict__ p3hi,
-                                                  const tw_t* __restrict__ pow_g, uint32_t lg_m) {
+                                                  const tw_t* __restrict__ pow_g, uint32_t lg_m,
+                                                  const tw_t* __restrict__ tw_full, const tw_t* __restrict__ zk_full) {
     extern __shared__ uint32_t smem[];
     constexpr uint32_t Lc = 1u << LOGLC, rowpad = Lc + (Lc >> 4);
     constexpr int REM = LOGLC - 4;                   // levels after the first radix-16 stage
@@ -947,10 +948,12 @@ __global__ void __launch_bounds__(256) k_ntt_invb(uint32_t* out, const uint32_t*
         const uint32_t* irow = in + (size_t)(R >> lg_rpp) * in_poly_stride + (size_t)(R & rpp_mask) * Lc;
         uint32_t* trow = tile + rr * rowpad;
         const uint32_t d1 = pow_g ? bitrev(R & rpp_mask, lg_rpp) : 0u;
+        const tw_t* tf = tw_full ? tw_full + (size_t)(R & rpp_mask) * Lc : nullptr;
         ntt_stage_io<4, LOGLC, true>(tw_g, w & ((1u << (LOGLC - 4)) - 1),
             [&](uint32_t b0, uint32_t d) {
                 uint32_t v = irow[b0 + d];
-                if (pow_g) {
+                if (tw_full) v = mul_tw(v, __ldg(tf + b0 + d));       // per-element table in data layout (get_full_table)
+                else if (pow_g) {
                     const uint32_t e = ((b0 + d) * d1) & mmask;
                     v = pow_apply(v, __ldg(plo + (e & lmask)), __ldg(phi + (e >> hh)));
                 }
@@ -986,7 +989,8 @@ __global__ void __launch_bounds__(256) k_ntt_invb(uint32_t* out, const uint32_t*
 #pragma unroll
                 for (int j = 0; j < (1 << KF); j++) {
                     v[j] = scale ? fp_mul(x[j], scale) : x[j];
-                    if (p3lo) {   // fused zk_shift (K2): slot holds degree d = bitrev(row) + rows_per_poly * bitrev(pos); multiply by 3^d
+                    if (p3lo && zk_full) v[j] = mul_tw(v[j], __ldg(zk_full + (size_t)(R & rpp_mask) * Lc + base + j));
+                    else if (p3lo) {   // fused zk_shift (K2): slot holds degree d = bitrev(row) + rows_per_poly * bitrev(pos); multiply by 3^d
                         const uint32_t d = bitrev(R & rpp_mask, lg_rpp) + (bitrev(base + j, LOGLC) << lg_rpp);
                         v[j] = pow_apply(v[j], __ldg(p3lo + (d & 4095)), __ldg(p3hi + (d >> 12)));
                     }
@@ -1249,9 +1253,11 @@ static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32
             return cudaGetLastError();
         }
         if (!DIF && pow_g && lg_m == logLc + lg_rpp && lg_rows == lg_rpp) tw_full = get_full_table(T, FULL_FWD, lg_m, lg_rpp);
+        if (DIF && pow_g && lg_m == logLc + lg_rpp) tw_full = get_full_table(T, FULL_INV, lg_m, lg_rpp);
+        if (DIF && p3lo) zk_full = get_full_table(T, FULL_ZK, logLc + lg_rpp, lg_rpp);
 #define B200_FUSED_CASE(LL) case LL: { cudaError_t e; \
             if (DIF) { auto kf = k_ntt_invb<LL>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
-                B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, scale, p3lo, p3hi, pow_g, lg_m); \
+                B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, scale, p3lo, p3hi, pow_g, lg_m, tw_full, zk_full); \
                 if (shift_done) *shift_done = p3lo != nullptr; } \
             else if (lg_e == 2) { auto kf = env_int("B200_NTT_FWD1_MINB", 6) == 5 ? k_ntt_fwd1<LL, 2, 5> : k_ntt_fwd1<LL, 2>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
                 if (scale) break; \

@@ -320,3 +320,44 @@ def test_batch_intt_large_against_the_oracle(gpu, b200lib, oracle, lg_n, count):
     ck(b200lib.b200_batch_ntt(ptr(d), lg_n, count, None))
     torch.cuda.synchronize()
     assert np.array_equal(host(d), a)
+
+
+# Every alternative route of the NTT launchers (read from the environment per launch) must give the oracle's words too: the radix-16 and
+# cp.async-staged strided passes, the radix-16 inverse pass B, the inter-pass twiddle in pass A's epilogue, the two-table twiddle /
+# zk_shift decomposition instead of the per-element tables, and a table-size cap below the transform size.
+NTT_ROUTES = [
+    {"B200_NTT_FULL": "0"},
+    {"B200_NTT_FULL_MAX_LG": "12"},
+    {"B200_NTT_INVB_R32": "0"},
+    {"B200_NTT_INVB_R32": "0", "B200_NTT_FULL": "0"},
+    {"B200_NTT_TW_IN_B": "0"},
+    {"B200_NTT_R32_DIRECT": "0"},
+    {"B200_NTT_R32_DIRECT": "0", "B200_NTT_TW_IN_B": "0", "B200_NTT_R32_MINB": "3"},
+    {"B200_NTT_R32": "0"},
+    {"B200_NTT_FUSED": "0"},
+    {"B200_NTT_INVB_R32_MINB": "4", "B200_NTT_R32D_MINB": "5", "B200_NTT_FWD1_MINB": "5", "B200_NTT_INVB_R32_WAVES": "1"},
+]
+
+
+@pytest.mark.parametrize("route", NTT_ROUTES, ids=lambda r: ",".join("%s=%s" % kv for kv in r.items()))
+def test_ntt_alternative_routes_bit_exact(gpu, b200lib, oracle, monkeypatch, route):
+    torch = gpu
+    for k, v in route.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(2024)
+    for lg_n, count in [(20, 2), (18, 3), (15, 4)]:
+        a = rand_elems(rng, count << lg_n, oracle)
+        ref = oracle.batch_intt(a, lg_n, count)
+        d = dev(torch, a)
+        ck(b200lib.b200_batch_intt(ptr(d), lg_n, count, None))
+        torch.cuda.synchronize()
+        assert np.array_equal(host(d), ref), (route, "intt", lg_n)
+        d = dev(torch, a)
+        ck(b200lib.b200_batch_intt_zk_shift(ptr(d), lg_n, count, None))
+        torch.cuda.synchronize()
+        assert np.array_equal(host(d), oracle.batch_zk_shift(ref, lg_n, count)), (route, "intt+shift", lg_n)
+        if lg_n <= 18 or count <= 2:
+            d_out = torch.zeros(count << (lg_n + 2), dtype=torch.int32, device="cuda")
+            ck(b200lib.b200_batch_expand_ntt(ptr(d_out), ptr(dev(torch, a)), lg_n, 2, count, None))
+            torch.cuda.synchronize()
+            assert np.array_equal(host(d_out), oracle.batch_expand_ntt(a, lg_n, count, 2)), (route, "expand", lg_n)
