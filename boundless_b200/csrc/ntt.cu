@@ -1259,7 +1259,7 @@ static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32
             if (DIF) { auto kf = k_ntt_invb<LL>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
                 B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, scale, p3lo, p3hi, pow_g, lg_m, tw_full, zk_full); \
                 if (shift_done) *shift_done = p3lo != nullptr; } \
-            else if (lg_e == 2) { auto kf = env_int("B200_NTT_FWD1_MINB", 6) == 5 ? k_ntt_fwd1<LL, 2, 5> : k_ntt_fwd1<LL, 2>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
+            else if (lg_e == 2) { auto kf = env_int("B200_NTT_FWD1_MINB", (tw_full || !pow_g) ? 6 : 5) == 5 ? k_ntt_fwd1<LL, 2, 5> : k_ntt_fwd1<LL, 2>; /* two-table twiddle: 5 CTAs leave the gathers their L1 */ e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
                 if (scale) break; \
                 B200_LAUNCH(kf)<<<grid, 256, sm, s>>>(out, in, rpc, lg_rpp, (uint32_t)total_rows, in_stride, out_stride, twt, pow_g, lg_m, lg_rows, tw_full); } \
             else { auto kf = k_ntt_fwd1<LL, 0>; e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
@@ -1288,8 +1288,14 @@ static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32
 
 // true when pass B of a two-pass inverse transform runs in the fused kernel k_ntt_invb (run_contig<true>'s first branch), which can
 // apply the inter-pass twiddle on load; B200_NTT_TW_IN_B=0 keeps it in pass A's epilogue (round 1's arrangement) for A/B timing
-static bool twiddle_in_pass_b(const uint32_t* d_io, uint32_t n2, size_t N) {
-    return n2 >= 8 && n2 <= 13 && env_int("B200_NTT_FUSED", 1) && env_int("B200_NTT_TW_IN_B", 1) && ((uintptr_t)d_io & 15) == 0 && N % 4 == 0;
+// Without a per-element table (sizes above B200_NTT_FULL_MAX_LG) the twiddle is two gathers from tables of up to 48 KB: that only pays
+// in pass B for rows of <= 1024 values -- the longer rows' kernels leave too little L1 beside their shared memory (2^23 / 2^24: 33 %
+// slower, profiles/ntt_sweep_r02_v7.jsonl against v8) -- so those sizes keep the twiddle in pass A's epilogue.
+static bool twiddle_in_pass_b(const DeviceTables* T, const uint32_t* d_io, uint32_t lg_n, uint32_t n1, size_t N) {
+    const uint32_t n2 = lg_n - n1;
+    if (!(n2 >= 8 && n2 <= 13 && env_int("B200_NTT_FUSED", 1) && env_int("B200_NTT_TW_IN_B", 1) && ((uintptr_t)d_io & 15) == 0 && N % 4 == 0))
+        return false;
+    return n2 <= 10 || get_full_table(T, FULL_INV, lg_n, n1) != nullptr;
 }
 
 cudaError_t launch_batch_intt(const DeviceTables* T, uint32_t* d_io, uint32_t lg_n, uint32_t count, cudaStream_t s) {
@@ -1310,7 +1316,7 @@ cudaError_t launch_batch_intt(const DeviceTables* T, uint32_t* d_io, uint32_t lg
         return launch_batch_intt(T, d_io, n2, count << BIG_N1, s);
     }
     const uint32_t n1 = split_n1(lg_n), n2 = lg_n - n1;
-    const bool tw_b = twiddle_in_pass_b(d_io, n2, N);
+    const bool tw_b = twiddle_in_pass_b(T, d_io, lg_n, n1, N);
     // pass A: DIF over i1 (rows of stride N2); the inter-pass twiddle (1/N folded into its table) here or on pass B's loads
     cudaError_t e = run_strided<true>(T, d_io, n1, 1u << n2, 1u << n2, count, N, tw_b ? nullptr : T->pow_inv[lg_n], lg_n, s);
     if (e != cudaSuccess) return e;
@@ -1335,7 +1341,7 @@ cudaError_t launch_batch_intt_shift(const DeviceTables* T, uint32_t* d_io, uint3
         e = run_contig<true>(T, d_io, d_io, lg_n, 0, 1, count, N, N, nullptr, 0, 0, scale, s, T->p3lo, T->p3hi, &done);
     } else {
         const uint32_t n1 = split_n1(lg_n), n2 = lg_n - n1;
-        const bool tw_b = twiddle_in_pass_b(d_io, n2, N);
+        const bool tw_b = twiddle_in_pass_b(T, d_io, lg_n, n1, N);
         e = run_strided<true>(T, d_io, n1, 1u << n2, 1u << n2, count, N, tw_b ? nullptr : T->pow_inv[lg_n], lg_n, s);
         if (e != cudaSuccess) return e;
         e = run_contig<true>(T, d_io, d_io, n2, 0, 1u << n1, count, N, N, tw_b ? T->pow_inv[lg_n] : nullptr, lg_n, 0, 0, s, T->p3lo, T->p3hi, &done);
