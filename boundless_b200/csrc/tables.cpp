@@ -113,9 +113,13 @@ const DeviceTables* get_tables(int device) {
 }
 
 static uint32_t h_bitrev(uint32_t x, uint32_t bits) {
-    uint32_t r = 0;
-    for (uint32_t i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
-    return r;
+    if (bits == 0) return 0;
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+    x = ((x >> 8) & 0x00ff00ffu) | ((x & 0x00ff00ffu) << 8);
+    x = (x >> 16) | (x << 16);
+    return x >> (32 - bits);
 }
 static int env_int_t(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
 
