@@ -4,6 +4,7 @@
 #include <stddef.h>
 #include <cuda_runtime.h>
 #include <atomic>
+#include <vector>
 
 namespace b200 {
 
@@ -52,6 +53,8 @@ enum { FULL_INV = 0, FULL_FWD = 1, FULL_ZK = 2 };
 // B200_NTT_FULL_MAX_LG (default 22), when B200_NTT_FULL=0, on allocation failure, or when the table of this size exists with another
 // split -- callers then use the two-table decomposition above.
 const uint2* get_full_table(const DeviceTables* T, int kind, uint32_t lg_m, uint32_t lg_rows);
+// the host computation behind it (Montgomery-form values; rou_* as in DeviceTables); used by get_full_table and by tests/host_emul
+void fill_full_table(int kind, uint32_t lg_m, uint32_t lg_rows, const uint32_t* rou_fwd, const uint32_t* rou_rev, std::vector<uint32_t>& v);
 const DeviceTables* get_tables(int device);   // lazily built, thread-safe; nullptr + error string on failure
 void free_tables();                           // b200_shutdown
 void compat_release();                        // b200_shutdown: scratch arena of the risc0-sys compatible supra_poly_divide (compat.cu)

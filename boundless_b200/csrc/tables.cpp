@@ -123,19 +123,14 @@ static uint32_t h_bitrev(uint32_t x, uint32_t bits) {
 }
 static int env_int_t(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
 
-const uint2* get_full_table(const DeviceTables* Tc, int kind, uint32_t lg_m, uint32_t lg_rows) {
-    if (kind < 0 || kind > 2 || lg_m > (uint32_t)MAX_LG || lg_rows > lg_m) return nullptr;
-    if (!env_int_t("B200_NTT_FULL", 1) || lg_m > (uint32_t)env_int_t("B200_NTT_FULL_MAX_LG", 22)) return nullptr;
-    DeviceTables* T = const_cast<DeviceTables*>(Tc);
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lk(mu);
-    if (T->full[kind][lg_m]) return T->full_rows[kind][lg_m] == lg_rows ? T->full[kind][lg_m] : nullptr;
+// Host computation of a per-element table (Montgomery form, index = rho * 2^(lg_m - lg_rows) + pos); see internal.h for the three kinds.
+// Separate from the upload so that tests/host_emul can check it against big-integer arithmetic without a device.
+void fill_full_table(int kind, uint32_t lg_m, uint32_t lg_rows, const uint32_t* rou_fwd, const uint32_t* rou_rev, std::vector<uint32_t>& v) {
     const uint32_t lg_cols = lg_m - lg_rows;
     const size_t n = (size_t)1 << lg_m;
-    std::vector<uint32_t> lo, hi, v(n);
-    uint32_t h;
+    v.resize(n);
+    std::vector<uint32_t> lo, hi;
     if (kind == FULL_ZK) {
-        h = 12;
         lo.resize(4096); hi.resize(lg_m > 12 ? (size_t)1 << (lg_m - 12) : 1);
         const uint32_t three = h_to_mont(3), step = h_pow(three, 4096);
         uint32_t cur = h_to_mont(1);
@@ -147,24 +142,35 @@ const uint2* get_full_table(const DeviceTables* Tc, int kind, uint32_t lg_m, uin
             const uint32_t d = h_bitrev(rho, lg_rows) + (h_bitrev(pos, lg_cols) << lg_rows);
             v[i] = h_mul(lo[d & 4095], hi[d >> 12]);
         }
-    } else {
-        // the same two factors get_tables() uploads for this size (normalisation folded into the inverse hi factor)
-        const bool inv = kind == FULL_INV;
-        h = (lg_m + 1) / 2;
-        const uint32_t w = inv ? T->rou_rev[lg_m] : T->rou_fwd[lg_m];
-        lo.resize((size_t)1 << h); hi.resize((size_t)1 << (lg_m - h));
-        uint32_t cur = h_to_mont(1);
-        for (auto& x : lo) { x = cur; cur = h_mul(cur, w); }
-        const uint32_t wh = h_pow(w, (uint64_t)1 << h);
-        cur = inv ? h_inv(h_to_mont(1u << (lg_m > (uint32_t)MAX_LG_2PASS ? (uint32_t)BIG_N1 : lg_m))) : h_to_mont(1);
-        for (auto& x : hi) { x = cur; cur = h_mul(cur, wh); }
-        const uint32_t mmask = (uint32_t)(n - 1), lmask = (1u << h) - 1;
-        for (size_t i = 0; i < n; i++) {
-            const uint32_t rho = (uint32_t)(i >> lg_cols), pos = (uint32_t)(i & (((size_t)1 << lg_cols) - 1));
-            const uint32_t e = (uint32_t)(((uint64_t)pos * h_bitrev(rho, lg_rows)) & mmask);
-            v[i] = h_mul(lo[e & lmask], hi[e >> h]);
-        }
+        return;
     }
+    // the same two factors get_tables() uploads for this size (normalisation folded into the inverse hi factor)
+    const bool inv = kind == FULL_INV;
+    const uint32_t h = (lg_m + 1) / 2;
+    const uint32_t w = inv ? rou_rev[lg_m] : rou_fwd[lg_m];
+    lo.resize((size_t)1 << h); hi.resize((size_t)1 << (lg_m - h));
+    uint32_t cur = h_to_mont(1);
+    for (auto& x : lo) { x = cur; cur = h_mul(cur, w); }
+    const uint32_t wh = h_pow(w, (uint64_t)1 << h);
+    cur = inv ? h_inv(h_to_mont(1u << (lg_m > (uint32_t)MAX_LG_2PASS ? (uint32_t)BIG_N1 : lg_m))) : h_to_mont(1);
+    for (auto& x : hi) { x = cur; cur = h_mul(cur, wh); }
+    const uint32_t mmask = (uint32_t)(n - 1), lmask = (1u << h) - 1;
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t rho = (uint32_t)(i >> lg_cols), pos = (uint32_t)(i & (((size_t)1 << lg_cols) - 1));
+        const uint32_t e = (uint32_t)(((uint64_t)pos * h_bitrev(rho, lg_rows)) & mmask);
+        v[i] = h_mul(lo[e & lmask], hi[e >> h]);
+    }
+}
+
+const uint2* get_full_table(const DeviceTables* Tc, int kind, uint32_t lg_m, uint32_t lg_rows) {
+    if (kind < 0 || kind > 2 || lg_m > (uint32_t)MAX_LG || lg_rows > lg_m) return nullptr;
+    if (!env_int_t("B200_NTT_FULL", 1) || lg_m > (uint32_t)env_int_t("B200_NTT_FULL_MAX_LG", 22)) return nullptr;
+    DeviceTables* T = const_cast<DeviceTables*>(Tc);
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (T->full[kind][lg_m]) return T->full_rows[kind][lg_m] == lg_rows ? T->full[kind][lg_m] : nullptr;
+    std::vector<uint32_t> v;
+    fill_full_table(kind, lg_m, lg_rows, T->rou_fwd, T->rou_rev, v);
     int prev = 0; cudaGetDevice(&prev);
     if (cudaSetDevice(T->device) != cudaSuccess) return nullptr;
     uint2* d = upload(v);
