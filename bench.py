@@ -177,11 +177,13 @@ def kernel_roofline(torch, L, pk):
         {"kernel": "expand+NTT 16 x 2^20 -> 2^22 (K3)", "ms": ms_e, "alg_gbs": 20.0 * cnt * (1 << n) / (ms_e * 1e-3) / 1e9},
         {"kernel": "iNTT 16 x 2^20 (K1)", "ms": ms_i, "alg_gbs": 8.0 * cnt * (1 << n) / (ms_i * 1e-3) / 1e9},
     ]
-    # both transforms are two 10-level passes: 5 butterfly + 2 inter-pass-twiddle multiplies per element in the first pass of each
-    # pair, 5 in the second -> 12 multiplies per (output) element, all by table constants (Shoup, 0.8 of a Montgomery multiply
-    # in multiplier-pipe cycles): on B200 that pipe, not HBM, is the binding roofline
-    kernels[0]["gmulmod_s"] = 0.8 * 12.0 * cnt * (4 << n) / (ms_e * 1e-3) / 1e9
-    kernels[1]["gmulmod_s"] = 0.8 * 12.0 * cnt * (1 << n) / (ms_i * 1e-3) / 1e9
+    # both transforms are two 10-level passes: 5 butterfly multiplies per element in each pass + 1 inter-pass-twiddle multiply (the
+    # per-element tables of round 2; 2 with the two-table decomposition, which these sizes no longer use) -> 11 multiplies per
+    # (output) element, all by table constants (Shoup, 0.8 of a Montgomery multiply in multiplier-pipe cycles): on B200 that pipe,
+    # not HBM, is the binding roofline
+    MULS_PER_ELEMENT = 11.0
+    kernels[0]["gmulmod_s"] = 0.8 * MULS_PER_ELEMENT * cnt * (4 << n) / (ms_e * 1e-3) / 1e9
+    kernels[1]["gmulmod_s"] = 0.8 * MULS_PER_ELEMENT * cnt * (1 << n) / (ms_i * 1e-3) / 1e9
     for k in kernels:
         k["frac_of_hbm_peak"] = k["alg_gbs"] / pk["hbm_gbs"]
         k["frac_of_int32_roofline"] = k["gmulmod_s"] / 3508.0
