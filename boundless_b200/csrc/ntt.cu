@@ -1269,6 +1269,9 @@ static cudaError_t run_contig(const DeviceTables* T, uint32_t* out, const uint32
         switch (logLc) { B200_FUSED_CASE(8) B200_FUSED_CASE(9) B200_FUSED_CASE(10) B200_FUSED_CASE(11) B200_FUSED_CASE(12) B200_FUSED_CASE(13) default: break; }
 #undef B200_FUSED_CASE
     }
+    // only the fused inverse kernels apply an inter-pass twiddle on their loads; twiddle_in_pass_b() asks for it under exactly their
+    // conditions, so reaching this point with one is a dispatch bug: fail instead of returning an untwiddled transform
+    if (DIF && pow_g) return cudaErrorInvalidValue;
     if (logLc >= 8 && logLc <= 13 && (DIF ? lg_e == 0 : lg_e == 2) && (1u << lg_rpp) == rows_per_poly) {
         const size_t sm = (size_t)rpc * (Lc + (Lc >> 4)) * 4;
 #define B200_CONTIG_CASE(LL) case LL: { auto kc = k_ntt_contig_c<LL, DIF ? 0 : 2, DIF>; \
