@@ -7,21 +7,25 @@
 // by 1/n; the forward transform maps bit-reversed coefficients to natural-order evaluations; `expand` is the
 // x4 replicate that equals zero padding in bit-reversed order, so the first lg_blowup levels are skipped.
 //
-// Design (B200): a size-2^m transform is two HBM passes (six-step): N = N1*N2.
-//   iNTT : pass A  strided tile [N1 rows][TW cols] in shared memory, DIF along rows, then the inter-pass
-//                  twiddle w^-(i0*bitrev(r)) (and the 1/N scale, folded into the twiddle table), in place;
-//          pass B  contiguous rows of N2, DIF, in place.
-//   fwd  : pass 1  contiguous row of N2 coefficients -> replicated x4 in shared memory -> DIT (levels above
-//                  the blow-up) -> inter-pass twiddle -> written as a row of 4*N2;
+// Design (B200): a size-2^m transform is two HBM passes (six-step): N = N1*N2 (three for 2^25 / 2^26).
+//   iNTT : pass A  strided tile [N1 rows][8 cols], DIF along rows, in place;
+//          pass B  contiguous rows of N2: the inter-pass twiddle w^-(i0*bitrev(r)) (with the 1/N scale folded in) on the loads, DIF,
+//                  optionally the zk_shift factor on the stores, in place.  (Sizes without a per-element table and rows > 1024 keep
+//                  the twiddle in pass A's epilogue, as in round 1.)
+//   fwd  : pass 1  contiguous row of N2 coefficients -> replicated x4 -> DIT (levels above the blow-up) -> inter-pass twiddle ->
+//                  written as a row of 4*N2;
 //          pass 2  strided tile, DIT along rows, in place.
-// Every pass moves each element HBM->smem->HBM once with >=32-byte runs; butterflies are radix-16 register
-// stages (4 levels per shared-memory round trip); stage twiddles come from one compact per-level table
-// (TMA-staged into shared memory in the persistent strided pass, read-only path elsewhere), inter-pass twiddles
-// from a two-table decomposition w^e = lo[e & mask] * hi[e >> h].
+// Every pass moves each element HBM -> registers / shared memory -> HBM once in >= 32-byte runs.  The hot shapes (1024-row strided
+// tiles, 1024-value rows) are radix-32 register kernels: two five-level stages with one exchange through shared memory; the other
+// shapes are radix-16 stages (4 levels per shared-memory round trip).  Stage twiddles come from one compact per-level table
+// (TMA-staged into shared memory in the strided passes, read-only path elsewhere); inter-pass twiddles and zk_shift factors from
+// per-element tables in data layout (one coalesced load + one multiply; tables.cpp get_full_table) or, above their size cap, from a
+// two-table decomposition w^e = lo[e & mask] * hi[e >> h].
 // Kernel families, fastest first (the host dispatch falls through to the next when a shape is not covered):
-//   k_ntt_strided_p / k_ntt_fwd1 / k_ntt_invb   compile-time sizes, persistent + double-buffered / fused passes
-//   k_ntt_strided_c / k_ntt_contig_c            compile-time sizes, one tile per CTA
-//   k_ntt_strided   / k_ntt_contig              runtime sizes (any 2^k)
+//   k_ntt_strided_r32d / k_ntt_invb_r32 / k_ntt_fwd1 / k_ntt_invb   the segment's shapes
+//   k_ntt_strided_r32 / k_ntt_strided_pf                            cp.async double-buffered persistent strided passes
+//   k_ntt_strided_c / k_ntt_contig_c                                compile-time sizes, one tile per CTA
+//   k_ntt_strided   / k_ntt_contig                                  runtime sizes (any 2^k)
 #include "internal.h"
 #include "field.cuh"
 #include <cstdlib>
